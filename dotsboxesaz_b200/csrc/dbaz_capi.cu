@@ -1,0 +1,349 @@
+// dbaz_capi.cu -- the extern "C" boundary declared in include/dbaz_b200.h.
+// Plain pointers and sizes only; no torch types.  Built in-tree for sm_100a:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC ...
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dbaz_game_kernels.cuh"
+#include "dbaz_tree_kernels.cuh"
+
+using namespace dbaz;
+
+struct dbaz_engine {
+    dbaz_config cfg;
+    Board board;
+    TreeArgs ta;
+    int apl, nw;
+    int n_sms;
+    size_t adv_smem;
+    const double* noise;  // caller-owned device buffer of the current search (may be null)
+    double coeff;
+    unsigned long long* d_status;
+    std::string err;
+};
+
+static std::string g_create_err;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int fail(dbaz_engine* e, const std::string& msg) {
+    if (e) e->err = msg; else g_create_err = msg;
+    return 1;
+}
+int cuda_fail(dbaz_engine* e, const char* what, cudaError_t st) {
+    return fail(e, std::string(what) + ": " + cudaGetErrorString(st));
+}
+
+#define DBAZ_CK(e, call)                                   \
+    do {                                                   \
+        cudaError_t st_ = (call);                          \
+        if (st_ != cudaSuccess) return cuda_fail((e), #call, st_); \
+    } while (0)
+
+inline cudaStream_t S(uint64_t h) { return reinterpret_cast<cudaStream_t>(h); }
+inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
+
+int upload_lut(dbaz_engine* e) {
+    // c0(N) = log((N + base + 1) / base) + cpuct with the host libm -- the same function CPython's
+    // math.log calls (mcts.py:92-93) -- so no device log ulp difference can flip an argmax.
+    std::vector<double> lut(e->ta.lut_size);
+    for (int n = 0; n < e->ta.lut_size; ++n)
+        lut[n] = std::log(((double)n + e->ta.cpuct_base + 1.0) / e->ta.cpuct_base) + e->ta.cpuct;
+    DBAZ_CK(e, cudaMemcpy(const_cast<double*>(e->ta.lut), lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int launch_ok(dbaz_engine* e, const char* what) {
+    cudaError_t st = cudaGetLastError();
+    if (st != cudaSuccess) return cuda_fail(e, what, st);
+    return 0;
+}
+
+}  // namespace
+
+// dispatch on (actions per lane, mask words)
+#define DBAZ_DISPATCH(e, EXPR)                                   \
+    do {                                                         \
+        if ((e)->apl == 1) { constexpr int APL = 1, NW = 1; EXPR; } \
+        else if ((e)->apl == 2) { constexpr int APL = 2, NW = 1; EXPR; } \
+        else if ((e)->apl == 3) { constexpr int APL = 3, NW = 2; EXPR; } \
+        else { constexpr int APL = 4, NW = 2; EXPR; }            \
+    } while (0)
+
+extern "C" {
+
+int dbaz_abi_version(void) { return DBAZ_ABI_VERSION; }
+int dbaz_sizeof_state(void) { return (int)sizeof(dbaz_state); }
+
+const char* dbaz_last_error(const dbaz_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
+    if (!cfg || !out) return fail(nullptr, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DBAZ_ABI_VERSION) return fail(nullptr, "ABI version mismatch");
+    const int L = cfg->board_l, C = cfg->board_c;
+    if (L < 1 || C < 1) return fail(nullptr, "board dimensions must be >= 1");
+    const int A = 2 * (L + 1) * (C + 1);
+    if (A > DBAZ_MAX_ACTIONS) return fail(nullptr, "board too large: 2*(L+1)*(C+1) must be <= 128");
+    if (L * C > 16000) return fail(nullptr, "board too large");
+    if (cfg->n_games < 1) return fail(nullptr, "n_games must be >= 1");
+    if (cfg->max_nodes < 2 || cfg->max_nodes > 65536) return fail(nullptr, "max_nodes must be in [2, 65536]");
+    int ndev = 0;
+    cudaError_t st = cudaGetDeviceCount(&ndev);
+    if (st != cudaSuccess || ndev == 0)
+        return fail(nullptr, std::string("no CUDA device: this engine has no CPU fallback (") + cudaGetErrorString(st) + ")");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "bad device ordinal");
+    DeviceGuard guard(cfg->device);
+
+    dbaz_engine* e = new dbaz_engine();
+    e->cfg = *cfg;
+    Board& b = e->board;
+    b.L = L; b.C = C; b.rows = L + 1; b.cols = C + 1; b.plane = b.rows * b.cols; b.A = A; b.nboxes = L * C; b.F = 3 * b.plane;
+    b.real[0] = b.real[1] = 0;
+    for (int a = 0; a < A; ++a) {
+        int p = a / b.plane, rem = a % b.plane, l = rem / b.cols, c = rem % b.cols;
+        bool real = p == 0 ? (c < C) : (l < L);
+        if (real) b.real[a >> 6] |= 1ull << (a & 63);
+    }
+    e->apl = (A + 31) / 32;
+    e->nw = A > 64 ? 2 : 1;
+    cudaDeviceProp prop;
+    if ((st = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) { cuda_fail(nullptr, "cudaGetDeviceProperties", st); delete e; return 1; }
+    e->n_sms = prop.multiProcessorCount;
+
+    TreeArgs& ta = e->ta;
+    std::memset(&ta, 0, sizeof(ta));
+    ta.n_trees = cfg->n_games;
+    ta.max_nodes = cfg->max_nodes;
+    ta.stride = 32 + 16 * A;
+    ta.lut_size = cfg->lut_size > 0 ? cfg->lut_size : 65536;
+    ta.cpuct = cfg->cpuct;
+    ta.cpuct_base = cfg->cpuct_base;
+    const size_t arena_bytes = (size_t)ta.n_trees * ta.max_nodes * ta.stride;
+    auto alloc = [&](void** p, size_t bytes, const char* what) -> bool {
+        cudaError_t s2 = cudaMalloc(p, bytes);
+        if (s2 != cudaSuccess) {
+            char buf[256];
+            std::snprintf(buf, sizeof buf, "cudaMalloc(%s, %zu bytes): %s", what, bytes, cudaGetErrorString(s2));
+            g_create_err = buf;
+            return false;
+        }
+        return true;
+    };
+    bool ok = alloc((void**)&ta.arena, arena_bytes, "node pool") &&
+              alloc((void**)&ta.trees, (size_t)ta.n_trees * sizeof(TreeRec), "tree table") &&
+              alloc((void**)&ta.root_prior, (size_t)ta.n_trees * A * sizeof(double), "root priors") &&
+              alloc((void**)&ta.path, (size_t)ta.n_trees * PATH_CAP * sizeof(uint32_t), "paths") &&
+              alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double), "log table") &&
+              alloc((void**)&e->d_status, 4 * sizeof(unsigned long long), "status");
+    if (!ok) { dbaz_engine_destroy(e); return 1; }
+    if (upload_lut(e)) { g_create_err = e->err; dbaz_engine_destroy(e); return 1; }
+
+    const int nwords = (ta.max_nodes + 31) >> 5;
+    e->adv_smem = (size_t)2 * nwords * 4 + (size_t)ta.max_nodes * 2;
+    if (e->adv_smem > 48 * 1024) {
+        cudaError_t s1 = cudaFuncSetAttribute(k_advance_roots<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
+        cudaError_t s2 = cudaFuncSetAttribute(k_advance_roots<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
+        if (s1 != cudaSuccess || s2 != cudaSuccess) { g_create_err = "cannot reserve shared memory for re-rooting"; dbaz_engine_destroy(e); return 1; }
+    }
+    // an all-empty-board root set so that the engine is usable right after create
+    k_reset_roots<<<blocks_for(ta.n_trees, 128), 128>>>(b, ta, nullptr);
+    if ((st = cudaDeviceSynchronize()) != cudaSuccess) { cuda_fail(nullptr, "k_reset_roots", st); dbaz_engine_destroy(e); return 1; }
+    *out = e;
+    return 0;
+}
+
+void dbaz_engine_destroy(dbaz_engine* e) {
+    if (!e) return;
+    DeviceGuard guard(e->cfg.device);
+    cudaFree(e->ta.arena);
+    cudaFree(e->ta.trees);
+    cudaFree(e->ta.root_prior);
+    cudaFree(e->ta.path);
+    cudaFree(const_cast<double*>(e->ta.lut));
+    cudaFree(e->d_status);
+    delete e;
+}
+
+int dbaz_engine_info(const dbaz_engine* e, int32_t* out8) {
+    if (!e || !out8) return 1;
+    out8[0] = e->board.L; out8[1] = e->board.C; out8[2] = e->board.A; out8[3] = e->board.F;
+    out8[4] = e->ta.n_trees; out8[5] = e->ta.max_nodes; out8[6] = e->ta.stride; out8[7] = e->n_sms;
+    return 0;
+}
+
+int dbaz_engine_set_cpuct(dbaz_engine* e, double cpuct, double cpuct_base) {
+    if (!e) return 1;
+    if (cpuct == e->ta.cpuct && cpuct_base == e->ta.cpuct_base) return 0;
+    DeviceGuard guard(e->cfg.device);
+    DBAZ_CK(e, cudaDeviceSynchronize());
+    e->ta.cpuct = cpuct; e->ta.cpuct_base = cpuct_base;
+    e->cfg.cpuct = cpuct; e->cfg.cpuct_base = cpuct_base;
+    return upload_lut(e);
+}
+
+/* ------------------------------------------------------------------ game */
+
+int dbaz_game_init(dbaz_engine* e, dbaz_state* states, int64_t n, uint64_t stream) {
+    if (!e) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    k_game_init<<<blocks_for(n, 256), 256, 0, S(stream)>>>(e->board, states, n);
+    return launch_ok(e, "k_game_init");
+}
+
+int dbaz_game_valid_moves(dbaz_engine* e, const dbaz_state* states, uint8_t* out, int64_t n, uint64_t stream) {
+    if (!e) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    if (e->nw == 1) k_game_valid<1><<<blocks_for(n, 256), 256, 0, S(stream)>>>(e->board, states, out, n);
+    else k_game_valid<2><<<blocks_for(n, 256), 256, 0, S(stream)>>>(e->board, states, out, n);
+    return launch_ok(e, "k_game_valid");
+}
+
+int dbaz_game_play(dbaz_engine* e, dbaz_state* states, const int32_t* moves, int32_t* n_closed, int32_t* closed_lc,
+                   int64_t n, uint64_t stream) {
+    if (!e) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    if (e->nw == 1) k_game_play<1><<<blocks_for(n, 256), 256, 0, S(stream)>>>(e->board, states, moves, n_closed, closed_lc, n);
+    else k_game_play<2><<<blocks_for(n, 256), 256, 0, S(stream)>>>(e->board, states, moves, n_closed, closed_lc, n);
+    return launch_ok(e, "k_game_play");
+}
+
+int dbaz_game_result(dbaz_engine* e, const dbaz_state* states, int8_t* out, int64_t n, uint64_t stream) {
+    if (!e) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    k_game_result<<<blocks_for(n, 256), 256, 0, S(stream)>>>(states, out, n);
+    return launch_ok(e, "k_game_result");
+}
+
+int dbaz_game_features(dbaz_engine* e, const dbaz_state* states, void* planes, int32_t dtype, int32_t layout, int64_t n,
+                       uint64_t stream) {
+    if (!e) return 1;
+    if (dtype < DBAZ_F32 || dtype > DBAZ_I16 || layout < 0 || layout > 1) return fail(e, "bad dtype/layout");
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    if (e->nw == 1) k_game_features<1><<<blocks_for(n * 32, 256), 256, 0, S(stream)>>>(e->board, states, planes, dtype, layout, n);
+    else k_game_features<2><<<blocks_for(n * 32, 256), 256, 0, S(stream)>>>(e->board, states, planes, dtype, layout, n);
+    return launch_ok(e, "k_game_features");
+}
+
+int dbaz_game_random_rollout(dbaz_engine* e, dbaz_state* states, uint64_t seed, uint64_t game0, int32_t* n_plies,
+                             uint8_t* moves, int32_t max_plies, int64_t n, uint64_t stream) {
+    if (!e) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    if (e->nw == 1) k_game_rollout<1><<<blocks_for(n, 128), 128, 0, S(stream)>>>(e->board, states, seed, game0, n_plies, moves, max_plies, n);
+    else k_game_rollout<2><<<blocks_for(n, 128), 128, 0, S(stream)>>>(e->board, states, seed, game0, n_plies, moves, max_plies, n);
+    return launch_ok(e, "k_game_rollout");
+}
+
+int dbaz_fake_nn(dbaz_engine* e, const dbaz_state* leaf_states, float* priors, float* values, int32_t kind, int64_t n,
+                 uint64_t stream) {
+    if (!e) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    k_fake_nn<<<blocks_for(n * 32, 256), 256, 0, S(stream)>>>(e->board, leaf_states, priors, values, kind, n);
+    return launch_ok(e, "k_fake_nn");
+}
+
+/* ---------------------------------------------------------------- search */
+
+int dbaz_search_reset_roots(dbaz_engine* e, const dbaz_state* root_states, uint64_t stream) {
+    if (!e || !root_states) return 1;
+    DeviceGuard guard(e->cfg.device);
+    k_reset_roots<<<blocks_for(e->ta.n_trees, 128), 128, 0, S(stream)>>>(e->board, e->ta, root_states);
+    e->noise = nullptr; e->coeff = 0.0;
+    return launch_ok(e, "k_reset_roots");
+}
+
+int dbaz_search_begin(dbaz_engine* e, const int32_t* num_reads, const double* noise, double coeff, uint64_t stream) {
+    if (!e || !num_reads) return 1;
+    DeviceGuard guard(e->cfg.device);
+    e->noise = noise; e->coeff = coeff;
+    const int grid = blocks_for(e->ta.n_trees, TREE_WARPS);
+    DBAZ_DISPATCH(e, (k_search_begin<APL, NW><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(e->board, e->ta, num_reads, noise, coeff)));
+    return launch_ok(e, "k_search_begin");
+}
+
+int dbaz_search_step(dbaz_engine* e, const float* priors, const float* values, void* planes, int32_t dtype, int32_t layout,
+                     dbaz_state* leaf_states, int8_t* leaf_kind, uint64_t stream) {
+    if (!e || !priors || !values || !planes) return 1;
+    if (dtype < DBAZ_F32 || dtype > DBAZ_I16 || layout < 0 || layout > 1) return fail(e, "bad dtype/layout");
+    DeviceGuard guard(e->cfg.device);
+    const int grid = blocks_for(e->ta.n_trees, TREE_WARPS);
+    DBAZ_DISPATCH(e, (k_search_step<APL, NW><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(
+                         e->board, e->ta, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, leaf_kind)));
+    return launch_ok(e, "k_search_step");
+}
+
+int dbaz_search_root_visits(dbaz_engine* e, int32_t* out, uint64_t stream) {
+    if (!e || !out) return 1;
+    DeviceGuard guard(e->cfg.device);
+    k_root_visits<<<blocks_for((int64_t)e->ta.n_trees * 32, 256), 256, 0, S(stream)>>>(e->board, e->ta, out);
+    return launch_ok(e, "k_root_visits");
+}
+
+int dbaz_search_root_children(dbaz_engine* e, float* W, double* priors, int32_t* sign, double* ucb, uint64_t stream) {
+    if (!e) return 1;
+    DeviceGuard guard(e->cfg.device);
+    const int grid = blocks_for((int64_t)e->ta.n_trees * 32, 256);
+    if (e->nw == 1) k_root_children<1><<<grid, 256, 0, S(stream)>>>(e->board, e->ta, W, priors, sign, ucb);
+    else k_root_children<2><<<grid, 256, 0, S(stream)>>>(e->board, e->ta, W, priors, sign, ucb);
+    return launch_ok(e, "k_root_children");
+}
+
+int dbaz_search_tree_stats(dbaz_engine* e, int32_t* stats8, float* root_W, float* q, uint64_t stream) {
+    if (!e) return 1;
+    DeviceGuard guard(e->cfg.device);
+    k_tree_stats<<<blocks_for(e->ta.n_trees, 128), 128, 0, S(stream)>>>(e->ta, stats8, root_W, q);
+    return launch_ok(e, "k_tree_stats");
+}
+
+int dbaz_search_root_states(dbaz_engine* e, dbaz_state* out, uint64_t stream) {
+    if (!e || !out) return 1;
+    DeviceGuard guard(e->cfg.device);
+    k_root_states<<<blocks_for(e->ta.n_trees, 128), 128, 0, S(stream)>>>(e->ta, out);
+    return launch_ok(e, "k_root_states");
+}
+
+int dbaz_search_advance_roots(dbaz_engine* e, const int32_t* moves, int32_t reuse, uint64_t stream) {
+    if (!e || !moves) return 1;
+    DeviceGuard guard(e->cfg.device);
+    if (e->nw == 1) k_advance_roots<1><<<e->ta.n_trees, ADV_THREADS, e->adv_smem, S(stream)>>>(e->board, e->ta, moves, reuse);
+    else k_advance_roots<2><<<e->ta.n_trees, ADV_THREADS, e->adv_smem, S(stream)>>>(e->board, e->ta, moves, reuse);
+    e->noise = nullptr; e->coeff = 0.0;
+    return launch_ok(e, "k_advance_roots");
+}
+
+int dbaz_search_status(dbaz_engine* e, int64_t* out4, uint64_t stream) {
+    if (!e) return 1;
+    DeviceGuard guard(e->cfg.device);
+    DBAZ_CK(e, cudaMemsetAsync(e->d_status, 0, 4 * sizeof(unsigned long long), S(stream)));
+    k_status<<<blocks_for(e->ta.n_trees, 128), 128, 0, S(stream)>>>(e->ta, e->d_status);
+    if (launch_ok(e, "k_status")) return 1;
+    unsigned long long h[4];
+    DBAZ_CK(e, cudaMemcpyAsync(h, e->d_status, sizeof h, cudaMemcpyDeviceToHost, S(stream)));
+    DBAZ_CK(e, cudaStreamSynchronize(S(stream)));
+    if (out4) for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
+    if (h[0]) {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "%llu tree(s) faulted: node pool exhausted (max_nodes=%d) or illegal re-root move",
+                      h[0], e->ta.max_nodes);
+        return fail(e, buf);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,683 @@
+// dbaz_tree_kernels.cuh -- the per-simulation hot path: PUCT select, lazy child creation,
+// feature gather, expand, backup, root-prior mix, re-root with in-place subtree compaction.
+//
+// One warp owns one tree (one game) and runs its simulations strictly in order, so no
+// atomics are needed and visit counts are bit-identical to the reference's
+// UCT_search(max_pending_evals=1); parallelism comes from the thousands of trees.
+//
+// HBM layout per tree t (arena[t] = max_nodes fixed-stride nodes):
+//   node i : [ dbaz_state header 32 B | Child rec[A] 16 B each ]      stride = 32 + 16*A
+// A node's own N/W live in its parent's Child record (as in mcts.py:67-89); the root's live
+// in TreeRec (TreeRoot, mcts.py:21-36).  Node 0 is always the root (re-rooting compacts the
+// kept subtree to the front of the arena), so Child.child == 0 means "not created".
+//
+// Reference behaviour restated (paths relative to the reference root):
+//   mcts.py:91-103   children_ucb_score / best_child  -> select_level()
+//   mcts.py:105-114  select_leaf                      -> tree_select()
+//   mcts.py:116-132  expand / backup                  -> tree_expand_backup()
+//   mcts.py:184-199  _search                          -> k_search_step
+//   mcts.py:205-229  UCT_search head (root prior mix) -> root_prior_mix()
+//   mcts.py:163-180  init_mcts_tree                   -> k_advance_roots
+#pragma once
+#include "dbaz_device.cuh"
+
+namespace dbaz {
+
+enum : uint32_t {
+    TF_PRIOR_SET = 1,      // root_prior[t] holds this root's child_priors (set by a UCT_search head)
+    TF_PRIOR_F64 = 2,      // ... and they were produced by float64 arithmetic
+    TF_PREP_PENDING = 4,   // root was unexpanded at begin(): mix priors after its first backup
+    TF_ERR_POOL = 8,       // node pool exhausted
+    TF_ERR_MOVE = 16,      // advance_roots with an illegal move
+};
+
+struct __align__(64) TreeRec {
+    int32_t n_nodes;
+    int32_t root_N;       // TreeRoot.child_number_visits[None]
+    float root_W;         // TreeRoot.child_total_value[None] (float32 in effect)
+    int32_t sims_left;
+    int32_t leaf;         // node waiting for its evaluation, -1 = none
+    int32_t path_len;
+    uint32_t flags;
+    int32_t max_deepness;
+    int32_t deepness_correction;
+    int32_t terminal_count;
+    int32_t tree_size;
+    int32_t root_sign;
+    unsigned long long total_sims, total_path;
+};
+static_assert(sizeof(TreeRec) == 64, "TreeRec must be 64 bytes");
+
+constexpr int PATH_CAP = 128;               // >= number of real edges + 1
+constexpr uint32_t PATH_ROOT = 0x7fffff00u; // parent field of the root's path element
+
+struct TreeArgs {
+    char* arena;          // n_trees * max_nodes * stride bytes
+    TreeRec* trees;
+    double* root_prior;   // [n_trees][A]
+    uint32_t* path;       // [n_trees][PATH_CAP]
+    const double* lut;    // c0(N) = log((N + base + 1)/base) + cpuct, host libm
+    int lut_size;
+    int n_trees;
+    int max_nodes;
+    int stride;           // node stride in bytes
+    double cpuct, cpuct_base;
+};
+
+__device__ __forceinline__ char* node_ptr(const TreeArgs& ta, int t, int i) {
+    return ta.arena + ((int64_t)t * ta.max_nodes + i) * (int64_t)ta.stride;
+}
+__device__ __forceinline__ dbaz_state load_hdr(const char* np) {
+    // 32-byte header as two 16-byte loads; every lane reads the same address (broadcast)
+    union { dbaz_state s; int4 v[2]; } u;
+    const int4* p = reinterpret_cast<const int4*>(np);
+    u.v[0] = p[0]; u.v[1] = p[1];
+    return u.s;
+}
+__device__ __forceinline__ void store_hdr(char* np, const dbaz_state& s) {
+    union { dbaz_state s; int4 v[2]; } u;
+    u.s = s;
+    int4* p = reinterpret_cast<int4*>(np);
+    p[0] = u.v[0]; p[1] = u.v[1];
+}
+__device__ __forceinline__ Child* node_children(char* np) { return reinterpret_cast<Child*>(np + 32); }
+
+__device__ __forceinline__ double puct_c0(const TreeArgs& ta, int N) {
+    if (N < ta.lut_size) return ta.lut[N];
+    // beyond the host table: device log (<= 1 ulp from libm; documented in DESIGN.md)
+    return __dadd_rn(log(__ddiv_rn(__dadd_rn(__dadd_rn((double)N, ta.cpuct_base), 1.0), ta.cpuct_base)), ta.cpuct);
+}
+
+// Per-lane constants of the lane -> action mapping (action = lane + 32*k): own bit and the two
+// boxes each action borders.  Computed once per kernel, reused at every level of every tree.
+template <int APL, int NW>
+struct LaneActions {
+    Mask<NW> box[APL][2];
+    bool real[APL];
+    __device__ __forceinline__ void init(const Board& b, int lane) {
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+            int a = lane + 32 * k;
+            int lc[2][2];
+            real[k] = a < b.A && ((b.real[a >> 6] >> (a & 63)) & 1ull);
+            if (a < b.A) action_boxes<NW>(b, a, box[k], lc);
+            else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) box[k][j].w[i] = 0;
+            }
+        }
+    }
+    // boxes closed by action k of this lane on edges e (before the move)
+    __device__ __forceinline__ int closes(int k, const Mask<NW>& e, int a) const {
+        Mask<NW> ea = e;
+        mask_set(ea, a);
+        return closed_count<NW>(ea, box[k]);
+    }
+};
+
+// One PUCT level (mcts.py:91-103), float64 with every operation individually rounded (no FMA):
+//   pb_c = c0(N) * (sqrt(N) / (n_i + 1)); score_i = pb_c * prior_i + (W_i / (1 + n_i)) * sign_i
+//   argmax over legal actions, lowest action id wins ties (np.argmax).
+template <int APL, int NW>
+__device__ __forceinline__ double ucb_score(double c0, double sq, const Child& c, double prior, int sign) {
+    double pb = __dmul_rn(c0, __ddiv_rn(sq, (double)(c.N + 1)));
+    double ps = __dmul_rn(pb, prior);
+    double vs = __dmul_rn(__ddiv_rn((double)c.W, (double)(1 + c.N)), (double)sign);
+    return __dadd_rn(ps, vs);
+}
+
+// Root prior mix, head of UCT_search (mcts.py:213-226).  Warp-cooperative; `sh` is a per-warp
+// shared scratch of A doubles.  noise == nullptr <=> alpha <= 0.
+template <int APL, int NW>
+__device__ __forceinline__ void root_prior_mix(const Board& b, const TreeArgs& ta, int t, TreeRec& T, const dbaz_state& rh,
+                                               const double* noise, double coeff, double* sh, int lane) {
+    const int A = b.A;
+    double* rp = ta.root_prior + (int64_t)t * A;
+    bool f64;
+    // source: the root's current child_priors
+    if (T.flags & TF_PRIOR_SET) {
+        f64 = T.flags & TF_PRIOR_F64;
+        for (int a = lane; a < A; a += 32) sh[a] = rp[a];
+    } else if ((rh.flags & NF_EXPANDED) && !(rh.flags & NF_TERMINAL)) {
+        f64 = false;
+        const Child* ch = node_children(node_ptr(ta, t, 0));
+        for (int a = lane; a < A; a += 32) sh[a] = (double)ch[a].prior;
+    } else {  // terminal root: np.zeros(A), float64
+        f64 = true;
+        for (int a = lane; a < A; a += 32) sh[a] = 0.0;
+    }
+    __syncwarp();
+    double probs[APL];
+    bool probs_f64;
+    if (f64) {
+        double s = np_sum<double>(sh, A);
+        probs_f64 = true;
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+            int a = lane + 32 * k;
+            probs[k] = (a < A) ? (s != 0.0 ? __ddiv_rn(sh[a], s) : 0.0) : 0.0;
+        }
+    } else {
+        // float32 arithmetic on float32 data: stage as floats in the same scratch
+        float* shf = reinterpret_cast<float*>(sh);
+        float mine[APL];
+#pragma unroll
+        for (int k = 0; k < APL; ++k) { int a = lane + 32 * k; mine[k] = a < A ? (float)sh[a] : 0.0f; }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < APL; ++k) { int a = lane + 32 * k; if (a < A) shf[a] = mine[k]; }
+        __syncwarp();
+        float s = np_sum<float>(shf, A);
+        probs_f64 = (s == 0.0f);  // np.zeros(len) is float64
+#pragma unroll
+        for (int k = 0; k < APL; ++k) probs[k] = (s != 0.0f) ? (double)__fdiv_rn(mine[k], s) : 0.0;
+    }
+    __syncwarp();
+    bool out_f64;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+        int a = lane + 32 * k;
+        if (a >= A) continue;
+        double r;
+        if (probs_f64) {
+            r = __dadd_rn(__dmul_rn(1.0 - coeff, probs[k]), __dmul_rn(coeff, noise ? noise[(int64_t)t * A + a] : 0.0));
+        } else if (noise) {
+            float c1 = (float)(1.0 - coeff);  // python float is "weak": float32 multiply
+            r = __dadd_rn((double)__fmul_rn(c1, (float)probs[k]), __dmul_rn(coeff, noise[(int64_t)t * A + a]));
+        } else {
+            float c1 = (float)(1.0 - coeff), z = (float)__dmul_rn(coeff, 0.0);
+            r = (double)__fadd_rn(__fmul_rn(c1, (float)probs[k]), z);
+        }
+        rp[a] = r;
+    }
+    out_f64 = probs_f64 || noise != nullptr;
+    T.flags = (T.flags & ~(TF_PRIOR_F64 | TF_PREP_PENDING)) | TF_PRIOR_SET | (out_f64 ? TF_PRIOR_F64 : 0u);
+    __syncwarp();
+}
+
+// expand + backup of the pending leaf (mcts.py:116-132 and the prior masking of 188-196)
+template <int APL, int NW>
+__device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArgs& ta, int t, TreeRec& T,
+                                                   const float* __restrict__ priors, const float* __restrict__ values,
+                                                   double* sh, int lane) {
+    const int A = b.A;
+    char* lp = node_ptr(ta, t, T.leaf);
+    dbaz_state lh = load_hdr(lp);
+    const bool terminal = lh.flags & NF_TERMINAL;
+    float value;
+    if (!terminal) {
+        // child_priors * valid (float32), NumPy-order sum, renormalise unless s == 1 or s <= 0
+        float* shf = reinterpret_cast<float*>(sh);
+        float p[APL];
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+            int a = lane + 32 * k;
+            if (a < A) {
+                float x = priors[(int64_t)t * A + a];
+                bool legal = ((b.real[NW == 1 ? 0 : (a >> 6)] & ~lh.edges[NW == 1 ? 0 : (a >> 6)]) >> (a & 63)) & 1ull;
+                p[k] = legal ? x : __fmul_rn(x, 0.0f);
+                shf[a] = p[k];
+            }
+        }
+        __syncwarp();
+        float s = np_sum<float>(shf, A);
+        __syncwarp();
+        Child* ch = node_children(lp);
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+            int a = lane + 32 * k;
+            if (a < A) {
+                float q = (s > 0.0f && s != 1.0f) ? __fdiv_rn(p[k], s) : p[k];
+                Child c; c.W = 0.0f; c.N = 0; c.prior = q; c.child = 0;
+                *reinterpret_cast<int4*>(&ch[a]) = *reinterpret_cast<int4*>(&c);
+            }
+        }
+        value = values[t];
+    } else {
+        value = (float)lh.result;  // get_result(): python int 1 / 0
+        if (T.leaf == 0) {
+            // a terminal ROOT is re-expanded with np.zeros(A) on every visit (mcts.py:195-198), which
+            // also discards whatever the UCT_search head mixed into its child_priors
+            double* rp = ta.root_prior + (int64_t)t * A;
+            for (int a = lane; a < A; a += 32) rp[a] = 0.0;
+            T.flags |= TF_PRIOR_SET | TF_PRIOR_F64;
+        }
+    }
+    if (!(lh.flags & NF_EXPANDED) && lane == 0) {
+        lh.flags |= NF_EXPANDED;
+        reinterpret_cast<int4*>(lp)[1] = reinterpret_cast<int4*>(&lh)[1];
+    }
+    // backup: every path node gets W += v*s + 1 and N += 1; all but the leaf also carry the
+    // virtual loss subtracted on the way down (W - 1 first, as its own float32 rounding step).
+    const uint32_t* path = ta.path + (int64_t)t * PATH_CAP;
+    const int plen = T.path_len;
+    for (int j = lane; j < plen; j += 32) {
+        uint32_t pe = path[j];
+        int tp = pe >> 31;
+        float v = (tp == (int)lh.to_play) ? value : -value;
+        float add = __fadd_rn(v, 1.0f);
+        bool is_leaf = (j == plen - 1);
+        if (j == 0) {
+            float W = T.root_W;
+            if (!is_leaf) W = __fsub_rn(W, 1.0f);
+            T.root_W = __fadd_rn(W, add);  // only lane 0 reaches j == 0; T is written back by lane 0
+            T.root_N += 1;
+        } else {
+            int parent = (pe & 0x7fffffffu) >> 8, act = pe & 0xffu;
+            float2* cell = reinterpret_cast<float2*>(&node_children(node_ptr(ta, t, parent))[act]);
+            float2 wn = *cell;
+            float W = wn.x;
+            if (!is_leaf) W = __fsub_rn(W, 1.0f);
+            wn.x = __fadd_rn(W, add);
+            wn.y = __int_as_float(__float_as_int(wn.y) + 1);
+            *cell = wn;
+        }
+    }
+    if (lane == 0) {
+        T.terminal_count += terminal ? 1 : 0;
+        T.max_deepness = max(T.max_deepness, (int)lh.depth);
+        if (T.leaf == 0) T.root_sign = (lh.to_play == (uint8_t)lh.just_played) ? 1 : -1;
+        T.leaf = -1;
+        T.total_sims += 1;
+        T.total_path += plen;
+    }
+}
+
+// select_leaf with lazy child creation (mcts.py:105-114).  Returns the leaf kind
+// (1 = needs evaluation, 2 = terminal) and leaves the leaf header in `leaf_hdr`.
+template <int APL, int NW>
+__device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, int t, TreeRec& T,
+                                           const LaneActions<APL, NW>& la, dbaz_state& leaf_hdr, int lane) {
+    const int A = b.A;
+    const double* rp = ta.root_prior + (int64_t)t * A;
+    int cur = 0, curN = T.root_N, depth = 0;
+    uint32_t* path = ta.path + (int64_t)t * PATH_CAP;  // published for the backup that follows the evaluation
+    int leaf = -1;
+    while (true) {
+        char* np = node_ptr(ta, t, cur);
+        dbaz_state h = load_hdr(np);
+        Child c[APL];
+        const bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
+        if (interior) {
+            const Child* ch = node_children(np);
+#pragma unroll
+            for (int k = 0; k < APL; ++k) {
+                int a = lane + 32 * k;
+                if (a < A) *reinterpret_cast<int4*>(&c[k]) = *reinterpret_cast<const int4*>(&ch[a]);
+            }
+        }
+        if (depth == 0 && lane == 0) path[0] = PATH_ROOT | ((uint32_t)h.to_play << 31);
+        if (!interior) { leaf = cur; leaf_hdr = h; break; }
+
+        Mask<NW> e = load_edges<NW>(h);
+        double c0 = puct_c0(ta, curN);
+        double sq = __dsqrt_rn((double)curN);
+        double best = -INFINITY;
+        int best_a = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+            int a = lane + 32 * k;
+            bool legal = la.real[k] && !mask_test(e, a < A ? a : 0);
+            if (legal) {
+                int sign = la.closes(k, e, a) ? 1 : -1;
+                double prior = (depth == 0) ? rp[a] : (double)c[k].prior;
+                double sc = ucb_score<APL, NW>(c0, sq, c[k], prior, sign);
+                if (best_a == 0x7fffffff || sc > best) { best = sc; best_a = a; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            int oa = __shfl_xor_sync(0xffffffffu, best_a, off);
+            bool take = (oa != 0x7fffffff) && (best_a == 0x7fffffff || ob > best || (ob == best && oa < best_a));
+            if (take) { best = ob; best_a = oa; }
+        }
+        const int a = best_a;  // a non-terminal node always has a legal move
+        const int owner = a & 31, kk = a >> 5;
+        int child = 0, childN = 0, ncl = 0;
+#pragma unroll
+        for (int k = 0; k < APL; ++k)
+            if (k == kk) { child = c[k].child; childN = c[k].N; ncl = la.closes(k, e, lane + 32 * k); }
+        child = __shfl_sync(0xffffffffu, child, owner);
+        childN = __shfl_sync(0xffffffffu, childN, owner);
+        ncl = __shfl_sync(0xffffffffu, ncl, owner);
+        const int child_tp = ncl ? h.to_play : 1 - h.to_play;
+        ++depth;
+        if (lane == 0) path[depth] = ((uint32_t)cur << 8) | (uint32_t)a | ((uint32_t)child_tp << 31);
+        if (child == 0) {
+            // lazily create the child (mcts.py:53-54 -> BoxesState.play, dots_boxes_game.py:91-94)
+            int idx = T.n_nodes;
+            if (idx >= ta.max_nodes) { T.flags |= TF_ERR_POOL; T.sims_left = 0; return 0; }
+            T.n_nodes = idx + 1;
+            dbaz_state ns = h;
+            state_apply<NW>(ns, a, ncl);
+            int r = state_result(ns);
+            ns.flags = (r != DBAZ_RESULT_NONE) ? NF_TERMINAL : 0;
+            ns.depth = h.depth + 1;
+            ns.parent = cur; ns.parent_action = (int16_t)a; ns.result = (int16_t)r;
+            char* cp = node_ptr(ta, t, idx);
+            if (lane == 0) store_hdr(cp, ns);
+            if (lane == owner) node_children(np)[a].child = idx;
+            leaf = idx; leaf_hdr = ns;
+            break;
+        }
+        cur = child; curN = childN;
+    }
+    T.leaf = leaf;
+    T.path_len = depth + 1;
+    return (leaf_hdr.flags & NF_TERMINAL) ? 2 : 1;
+}
+
+// ---------------------------------------------------------------- kernels
+constexpr int TREE_WARPS = 4;  // trees per CTA
+
+template <int APL, int NW>
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, const double* __restrict__ noise, double coeff) {
+    __shared__ double sh_all[TREE_WARPS][DBAZ_MAX_ACTIONS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * TREE_WARPS + warp;
+    if (t >= ta.n_trees) return;
+    TreeRec T = ta.trees[t];
+    const int nr = num_reads[t];
+    T.leaf = -1;
+    if (nr < 0) {
+        T.sims_left = 0;
+        T.flags &= ~TF_PREP_PENDING;
+    } else {
+        dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
+        if (rh.flags & NF_EXPANDED) {
+            root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh_all[warp], lane);
+            T.sims_left = nr;
+        } else {
+            T.flags |= TF_PREP_PENDING;  // mcts.py:207-208: one extra _search() first
+            T.sims_left = nr + 1;
+        }
+    }
+    if (lane == 0) ta.trees[t] = T;
+}
+
+template <int APL, int NW>
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+k_search_step(Board b, TreeArgs ta, const float* __restrict__ priors, const float* __restrict__ values,
+              const double* __restrict__ noise, double coeff, void* __restrict__ planes, int dtype, int layout,
+              dbaz_state* __restrict__ leaf_states, int8_t* __restrict__ leaf_kind) {
+    __shared__ double sh_all[TREE_WARPS][DBAZ_MAX_ACTIONS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * TREE_WARPS + warp;
+    if (t >= ta.n_trees) return;
+    TreeRec T = ta.trees[t];
+    if (T.leaf < 0 && T.sims_left <= 0) {  // idle tree: nothing to read or write
+        if (leaf_kind && lane == 0) leaf_kind[t] = 0;
+        return;
+    }
+    double* sh = sh_all[warp];
+    if (T.leaf >= 0) {
+        tree_expand_backup<APL, NW>(b, ta, t, T, priors, values, sh, lane);
+        // lane 0 owns the authoritative TreeRec; re-broadcast the fields the other lanes need
+        T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
+        T.leaf = -1;
+        __syncwarp();
+        if (T.flags & TF_PREP_PENDING) {
+            dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
+            root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
+        }
+    }
+    int kind = 0;
+    if (T.sims_left > 0) {
+        LaneActions<APL, NW> la;
+        la.init(b, lane);
+        dbaz_state lh;
+        __syncwarp();  // backup stores above must be visible to the selection loads below
+        kind = tree_select<APL, NW>(b, ta, t, T, la, lh, lane);
+        if (kind) {
+            T.sims_left -= 1;
+            write_planes_warp<NW>(b, lh, planes, t, dtype, layout, lane);
+            if (leaf_states && lane == 0) {
+                dbaz_state pub = lh;
+                pub.flags = 0; pub.depth = 0; pub.parent = -1; pub.parent_action = -1;
+                store_hdr(reinterpret_cast<char*>(&leaf_states[t]), pub);
+            }
+        }
+    }
+    if (lane == 0) {
+        ta.trees[t] = T;
+        if (leaf_kind) leaf_kind[t] = (int8_t)kind;
+    }
+}
+
+// create_root_uct_node for every tree
+__global__ void k_reset_roots(Board b, TreeArgs ta, const dbaz_state* __restrict__ roots) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ta.n_trees) return;
+    dbaz_state s;
+    if (roots) s = roots[t];
+    else state_init(b, s);  // empty board
+    int r = state_result(s);
+    s.flags = (r != DBAZ_RESULT_NONE) ? NF_TERMINAL : 0;
+    s.depth = 1;  // TreeRoot.deepness (0) + 1, mcts.py:64-65
+    s.parent = -1; s.parent_action = -1; s.result = (int16_t)r;
+    store_hdr(node_ptr(ta, t, 0), s);
+    TreeRec T;
+    T.n_nodes = 1; T.root_N = 0; T.root_W = 0.0f; T.sims_left = 0; T.leaf = -1; T.path_len = 0; T.flags = 0;
+    T.max_deepness = 0; T.deepness_correction = 0; T.terminal_count = 0; T.tree_size = 0; T.root_sign = 0;
+    T.total_sims = 0; T.total_path = 0;
+    ta.trees[t] = T;
+}
+
+// init_mcts_tree (mcts.py:163-180).  One CTA per tree.  With reuse the kept subtree is compacted
+// in place: (1) reachability by parent pointers (a child always has a larger index than its
+// parent, so a fixed point over "marked[parent]" converges in <= height rounds, in shared
+// memory); (2) prefix sum of the mark bits gives new indices; (3) nodes move front-to-back in
+// chunks of one node per warp (all loads of a chunk complete before its stores; new <= old so
+// nothing unread is overwritten), remapping parent and child indices on the fly.
+constexpr int ADV_THREADS = 256;
+template <int NW>
+__global__ void __launch_bounds__(ADV_THREADS)
+k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reuse) {
+    extern __shared__ uint32_t smem_u32[];
+    const int t = blockIdx.x;
+    const int mv = moves[t];
+    if (mv < 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwords = (ta.max_nodes + 31) >> 5;
+    uint32_t* mark = smem_u32;                 // [nwords]
+    uint32_t* prefix = smem_u32 + nwords;      // [nwords]
+    uint16_t* parent16 = reinterpret_cast<uint16_t*>(smem_u32 + 2 * nwords);  // [max_nodes]
+    __shared__ int s_changed, s_total;
+    __shared__ TreeRec sT;
+    __shared__ dbaz_state s_root;
+    __shared__ Child s_entry;
+
+    if (tid == 0) {
+        sT = ta.trees[t];
+        s_root = load_hdr(node_ptr(ta, t, 0));
+        if (mv < b.A) s_entry = node_children(node_ptr(ta, t, 0))[mv];
+    }
+    __syncthreads();
+    TreeRec T = sT;
+    dbaz_state rh = s_root;
+    if (!state_legal<NW>(b, rh, mv)) {
+        if (tid == 0) { T.flags |= TF_ERR_MOVE; ta.trees[t] = T; }
+        return;
+    }
+    const bool root_interior = (rh.flags & NF_EXPANDED) && !(rh.flags & NF_TERMINAL);
+    const int child = root_interior ? s_entry.child : 0;
+    const int nb_visits = root_interior ? s_entry.N : 0;
+    const int n = T.n_nodes;
+
+    if (child == 0 || !reuse) {
+        if (tid == 0) {
+            Mask<NW> box[2]; int lc[2][2];
+            action_boxes<NW>(b, mv, box, lc);
+            Mask<NW> e = load_edges<NW>(rh);
+            mask_set(e, mv);
+            dbaz_state ns = rh;
+            state_apply<NW>(ns, mv, closed_count<NW>(e, box));
+            int r = state_result(ns);
+            ns.flags = (r != DBAZ_RESULT_NONE) ? NF_TERMINAL : 0;
+            ns.depth = reuse ? rh.depth + 1 : 1;
+            ns.parent = -1; ns.parent_action = (int16_t)mv; ns.result = (int16_t)r;
+            store_hdr(node_ptr(ta, t, 0), ns);
+            T.n_nodes = 1;
+            T.deepness_correction = reuse ? ns.depth : 0;
+            T.tree_size = reuse ? nb_visits : 0;
+        }
+    } else {
+        for (int w = tid; w < nwords; w += ADV_THREADS) mark[w] = 0;
+        for (int i = tid; i < n; i += ADV_THREADS) {
+            int p = reinterpret_cast<const dbaz_state*>(node_ptr(ta, t, i))->parent;
+            parent16[i] = (uint16_t)(p < 0 ? 0 : p);
+        }
+        __syncthreads();
+        if (tid == 0) mark[child >> 5] = 1u << (child & 31);
+        __syncthreads();
+        while (true) {
+            if (tid == 0) s_changed = 0;
+            __syncthreads();
+            for (int i = child + 1 + tid; i < n; i += ADV_THREADS) {
+                if (!((mark[i >> 5] >> (i & 31)) & 1u)) {
+                    int p = parent16[i];
+                    if ((mark[p >> 5] >> (p & 31)) & 1u) { atomicOr(&mark[i >> 5], 1u << (i & 31)); s_changed = 1; }
+                }
+            }
+            __syncthreads();
+            if (!s_changed) break;
+            __syncthreads();
+        }
+        if (tid == 0) {  // nwords <= 1024: a serial scan is a few microseconds
+            int acc = 0;
+            for (int w = 0; w < nwords; ++w) { prefix[w] = acc; acc += __popc(mark[w]); }
+            s_total = acc;
+        }
+        __syncthreads();
+        auto newidx = [&](int i) { return (int)(prefix[i >> 5] + __popc(mark[i >> 5] & ((1u << (i & 31)) - 1u))); };
+        const int pieces = ta.stride >> 4;  // 16-byte pieces per node: 2 header + A children
+        constexpr int NWARPS = ADV_THREADS / 32;
+        constexpr int MAXP = (2 + DBAZ_MAX_ACTIONS + 31) / 32;
+        for (int base = child; base < n; base += NWARPS) {
+            const int i = base + warp;
+            const bool live = i < n && ((mark[i >> 5] >> (i & 31)) & 1u);
+            int4 buf[MAXP];
+            int npc = 0;
+            if (live) {
+                const int4* src = reinterpret_cast<const int4*>(node_ptr(ta, t, i));
+                const uint8_t fl = reinterpret_cast<const dbaz_state*>(src)->flags;
+                // unexpanded / terminal nodes have no meaningful child records: move the header only
+                npc = ((fl & NF_EXPANDED) && !(fl & NF_TERMINAL)) ? pieces : 2;
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q) {
+                    int pc = lane + 32 * q;
+                    if (pc < npc) {
+                        int4 v = src[pc];
+                        if (pc == 1) v.z = (i == child) ? -1 : newidx(v.z);   // header.parent
+                        else if (pc >= 2 && v.w != 0) v.w = newidx(v.w);      // Child.child
+                        buf[q] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            if (live) {
+                int4* dst = reinterpret_cast<int4*>(node_ptr(ta, t, newidx(i)));
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q) {
+                    int pc = lane + 32 * q;
+                    if (pc < npc) dst[pc] = buf[q];
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            T.n_nodes = s_total;
+            T.deepness_correction = reinterpret_cast<const dbaz_state*>(node_ptr(ta, t, 0))->depth;
+            T.tree_size = nb_visits;
+        }
+    }
+    if (tid == 0) {
+        T.root_N = 0; T.root_W = 0.0f; T.root_sign = 0; T.leaf = -1; T.path_len = 0; T.sims_left = 0;
+        T.max_deepness = 0; T.terminal_count = 0;
+        T.flags &= ~(TF_PRIOR_SET | TF_PRIOR_F64 | TF_PREP_PENDING);
+        ta.trees[t] = T;
+    }
+}
+
+// ------------------------------------------------------------ root views
+// root.child_number_visits (mcts.py:244): one warp per tree, coalesced row store
+__global__ void k_root_visits(Board b, TreeArgs ta, int32_t* __restrict__ out) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= ta.n_trees) return;
+    char* np = node_ptr(ta, w, 0);
+    dbaz_state h = load_hdr(np);
+    bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
+    const Child* ch = node_children(np);
+    for (int a = lane; a < b.A; a += 32) out[(int64_t)w * b.A + a] = interior ? ch[a].N : 0;
+}
+
+template <int NW>
+__global__ void k_root_children(Board b, TreeArgs ta, float* __restrict__ W, double* __restrict__ priors,
+                                int32_t* __restrict__ sign, double* __restrict__ ucb) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= ta.n_trees) return;
+    const int A = b.A;
+    char* np = node_ptr(ta, w, 0);
+    dbaz_state h = load_hdr(np);
+    TreeRec T = ta.trees[w];
+    bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
+    const Child* ch = node_children(np);
+    Mask<NW> e = load_edges<NW>(h);
+    double c0 = puct_c0(ta, T.root_N), sq = __dsqrt_rn((double)T.root_N);
+    for (int a = lane; a < A; a += 32) {
+        Child c; c.W = 0.0f; c.N = 0; c.prior = 0.0f; c.child = 0;
+        if (interior) c = ch[a];
+        double pr = (T.flags & TF_PRIOR_SET) ? ta.root_prior[(int64_t)w * A + a] : (double)c.prior;
+        int sg = 1;  // child_player_changed defaults to +1 until the child is expanded (mcts.py:61-62,119)
+        if (c.child != 0) {
+            dbaz_state chd = load_hdr(node_ptr(ta, w, c.child));
+            if (chd.flags & NF_EXPANDED) sg = (chd.to_play == (uint8_t)chd.just_played) ? 1 : -1;
+        }
+        int64_t o = (int64_t)w * A + a;
+        if (W) W[o] = c.W;
+        if (priors) priors[o] = pr;
+        if (sign) sign[o] = sg;
+        if (ucb) ucb[o] = ucb_score<1, NW>(c0, sq, c, pr, sg);
+    }
+    (void)e;
+}
+
+__global__ void k_tree_stats(TreeArgs ta, int32_t* __restrict__ stats8, float* __restrict__ root_W, float* __restrict__ q) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ta.n_trees) return;
+    TreeRec T = ta.trees[t];
+    dbaz_state h = load_hdr(node_ptr(ta, t, 0));
+    if (stats8) {
+        int32_t* o = stats8 + (int64_t)t * 8;
+        o[0] = T.root_N; o[1] = T.max_deepness - T.deepness_correction; o[2] = T.tree_size; o[3] = T.terminal_count;
+        o[4] = (h.flags & NF_EXPANDED) ? 1 : 0; o[5] = (h.flags & NF_TERMINAL) ? 1 : 0; o[6] = T.n_nodes;
+        o[7] = (int32_t)(T.flags & (TF_ERR_POOL | TF_ERR_MOVE));
+    }
+    if (root_W) root_W[t] = T.root_W;
+    if (q) q[t] = __fdiv_rn(T.root_W, (float)(1 + T.root_N));  // mcts.py:35
+}
+
+__global__ void k_root_states(TreeArgs ta, dbaz_state* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ta.n_trees) return;
+    dbaz_state h = load_hdr(node_ptr(ta, t, 0));
+    h.flags = 0; h.depth = 0; h.parent = -1; h.parent_action = -1; h.result = (int16_t)state_result(h);
+    out[t] = h;
+}
+
+// {errored trees, total sims, total path nodes, max n_nodes} by atomics into out4 (zeroed by the host)
+__global__ void k_status(TreeArgs ta, unsigned long long* __restrict__ out4) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ta.n_trees) return;
+    TreeRec T = ta.trees[t];
+    if (T.flags & (TF_ERR_POOL | TF_ERR_MOVE)) atomicAdd(&out4[0], 1ull);
+    atomicAdd(&out4[1], T.total_sims);
+    atomicAdd(&out4[2], T.total_path);
+    atomicMax(&out4[3], (unsigned long long)T.n_nodes);
+}
+
+}  // namespace dbaz

@@ -1,0 +1,288 @@
+"""Host-side handle of the CUDA engine: batched game rules and lock-step tree search.
+
+PyTorch is used for device memory, streams and CUDA graphs only; every rule and every tree
+operation runs in the hand-written sm_100a kernels behind include/dbaz_b200.h.  There is no
+CPU path: constructing an Engine without a CUDA device raises RuntimeError.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import STATE_DTYPE, RESULT_NONE
+
+_DTYPE_CODE = {torch.float32: _capi.F32, torch.float16: _capi.F16, torch.bfloat16: _capi.BF16, torch.int16: _capi.I16}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine = one GPU's shard of concurrent games (`n_games` trees of at most `max_nodes` nodes).
+
+    States are device tensors of shape [n, 4] int64 (32 packed bytes each, see STATE_DTYPE).
+    """
+
+    def __init__(self, board=(3, 3), n_games=1, max_nodes=8192, cpuct=(1.25, 19652), device=None, lut_size=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dotsboxesaz_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _capi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("dotsboxesaz_b200 engines live on CUDA devices only")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        cfg = _capi.Config(1, dev_index, int(board[0]), int(board[1]), int(n_games), int(max_nodes), int(lut_size), 0,
+                           float(cpuct[0]), float(cpuct[1]))
+        h = C.c_void_p()
+        torch.cuda.init()
+        if self.lib.dbaz_engine_create(C.byref(cfg), C.byref(h)) != 0:
+            raise EngineError(self.lib.dbaz_last_error(None).decode())
+        self._h = h
+        info = (C.c_int32 * 8)()
+        self.lib.dbaz_engine_info(self._h, info)
+        self.L, self.C, self.A, self.F, self.n_games, self.max_nodes, self.node_bytes, self.n_sms = list(info)
+        self.rows, self.cols = self.L + 1, self.C + 1
+        self.cpuct = (float(cpuct[0]), float(cpuct[1]))
+        # search I/O buffers (fixed addresses, so the wave loop can be captured in a CUDA graph)
+        self.priors = torch.zeros((n_games, self.A), dtype=torch.float32, device=self.device)
+        self.values = torch.zeros((n_games,), dtype=torch.float32, device=self.device)
+        self.leaf_states = torch.zeros((n_games, 4), dtype=torch.int64, device=self.device)
+        self.leaf_kind = torch.zeros((n_games,), dtype=torch.int8, device=self.device)
+        self.planes = None
+        self._plane_cfg = None
+        self._noise = None  # keeps the caller's noise buffer alive while the engine may read it
+        self._num_reads = torch.zeros((n_games,), dtype=torch.int32, device=self.device)
+        self.set_planes(torch.float32, channels_last=False)
+
+    # ------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dbaz_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_uint64(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.dbaz_last_error(self._h).decode())
+
+    def _states_arg(self, states):
+        if states.dtype != torch.int64 or states.dim() != 2 or states.shape[1] != 4 or not states.is_contiguous() \
+                or states.device != self.device:
+            raise ValueError("states must be a contiguous int64 [n, 4] tensor on %s" % self.device)
+        return states
+
+    def set_cpuct(self, cpuct):
+        """mcts.py:205 -- UCT_search re-assigns the PUCT constants on every call."""
+        cpuct = (float(cpuct[0]), float(cpuct[1]))
+        if cpuct != self.cpuct:
+            self._ck(self.lib.dbaz_engine_set_cpuct(self._h, cpuct[0], cpuct[1]))
+            self.cpuct = cpuct
+
+    def set_planes(self, dtype=torch.float32, channels_last=False):
+        """Choose dtype/layout of the leaf feature tensor the select kernel writes (the net's input)."""
+        cfg = (dtype, bool(channels_last))
+        if cfg != self._plane_cfg:
+            if channels_last:
+                base = torch.zeros((self.n_games, self.rows, self.cols, 3), dtype=dtype, device=self.device)
+                self.planes = base.permute(0, 3, 1, 2)  # logical NCHW view over NHWC memory
+                self._planes_base = base
+            else:
+                self.planes = torch.zeros((self.n_games, 3, self.rows, self.cols), dtype=dtype, device=self.device)
+                self._planes_base = self.planes
+            self._plane_cfg = cfg
+        return self.planes
+
+    # ---------------------------------------------------------- state I/O
+    def states_from_numpy(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=STATE_DTYPE).reshape(-1)
+        return torch.from_numpy(arr.view(np.int64).reshape(-1, 4).copy()).to(self.device)
+
+    @staticmethod
+    def states_to_numpy(states):
+        return states.detach().cpu().numpy().reshape(-1).view(STATE_DTYPE).copy()
+
+    # ---------------------------------------------------------- game rules
+    def new_states(self, n):
+        """BoxesState() x n (dots_boxes_game.py:30-39)."""
+        st = torch.empty((n, 4), dtype=torch.int64, device=self.device)
+        self._ck(self.lib.dbaz_game_init(self._h, _ptr(st), n, self._stream()))
+        return st
+
+    def valid_moves(self, states):
+        """get_valid_moves (dots_boxes_game.py:44-49) -> bool [n, A]."""
+        states = self._states_arg(states)
+        out = torch.empty((states.shape[0], self.A), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.dbaz_game_valid_moves(self._h, _ptr(states), _ptr(out), states.shape[0], self._stream()))
+        return out.bool()
+
+    def play(self, states, moves):
+        """play_ (dots_boxes_game.py:61-89) in place.  Returns (n_closed int32[n] with -1 where the
+        reference raises ValueError, closed_lc int32[n, 4])."""
+        states = self._states_arg(states)
+        n = states.shape[0]
+        moves = torch.as_tensor(moves, dtype=torch.int32, device=self.device).contiguous()
+        if moves.shape != (n,):
+            raise ValueError("moves must have shape [n]")
+        ncl = torch.empty((n,), dtype=torch.int32, device=self.device)
+        lc = torch.empty((n, 4), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.dbaz_game_play(self._h, _ptr(states), _ptr(moves), _ptr(ncl), _ptr(lc), n, self._stream()))
+        return ncl, lc
+
+    def result(self, states):
+        """get_result (dots_boxes_game.py:51-59) -> int8 [n], RESULT_NONE (2) for None."""
+        states = self._states_arg(states)
+        out = torch.empty((states.shape[0],), dtype=torch.int8, device=self.device)
+        self._ck(self.lib.dbaz_game_result(self._h, _ptr(states), _ptr(out), states.shape[0], self._stream()))
+        return out
+
+    def features(self, states, dtype=torch.int16, channels_last=False):
+        """get_features + nn_batch_builder (dots_boxes_game.py:96-100,148-155) -> [n, 3, L+1, C+1]."""
+        states = self._states_arg(states)
+        n = states.shape[0]
+        if channels_last:
+            base = torch.empty((n, self.rows, self.cols, 3), dtype=dtype, device=self.device)
+            out = base.permute(0, 3, 1, 2)
+        else:
+            base = out = torch.empty((n, 3, self.rows, self.cols), dtype=dtype, device=self.device)
+        self._ck(self.lib.dbaz_game_features(self._h, _ptr(states), _ptr(base), _DTYPE_CODE[dtype],
+                                             _capi.NHWC if channels_last else _capi.NCHW, n, self._stream()))
+        return out
+
+    def random_rollout(self, states, seed=0, game0=0, record_moves=False):
+        """Uniform random legal playouts to terminal, in place.  Returns n_plies (and the move lists)."""
+        states = self._states_arg(states)
+        n = states.shape[0]
+        plies = torch.empty((n,), dtype=torch.int32, device=self.device)
+        max_plies = self.A
+        moves = torch.full((n, max_plies), 255, dtype=torch.uint8, device=self.device) if record_moves else None
+        self._ck(self.lib.dbaz_game_random_rollout(self._h, _ptr(states), seed, game0, _ptr(plies), _ptr(moves), max_plies,
+                                                   n, self._stream()))
+        return (plies, moves) if record_moves else plies
+
+    def fake_nn(self, leaf_states, kind=0, priors=None, values=None):
+        """Deterministic stand-in for the net (tests / parity runs), see include/dbaz_b200.h."""
+        leaf_states = self._states_arg(leaf_states)
+        n = leaf_states.shape[0]
+        if priors is None:
+            priors = torch.empty((n, self.A), dtype=torch.float32, device=self.device)
+        if values is None:
+            values = torch.empty((n,), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.dbaz_fake_nn(self._h, _ptr(leaf_states), _ptr(priors), _ptr(values), int(kind), n, self._stream()))
+        return priors, values
+
+    # -------------------------------------------------------------- search
+    def reset_roots(self, states=None):
+        """create_root_uct_node (mcts.py:156-160) for every tree."""
+        if states is None:
+            states = self.new_states(self.n_games)
+        states = self._states_arg(states)
+        if states.shape[0] != self.n_games:
+            raise ValueError("need one root state per game")
+        self._noise = None
+        self._ck(self.lib.dbaz_search_reset_roots(self._h, _ptr(states), self._stream()))
+
+    def begin(self, num_reads, noise=None, coeff=0.0):
+        """Head of UCT_search (mcts.py:205-229).  num_reads: int or int32[n_games] (-1 = idle tree).
+        noise: float64 [n_games, A] Dirichlet sample times legal mask, or None (alpha <= 0)."""
+        if isinstance(num_reads, int):
+            self._num_reads.fill_(num_reads)
+        else:
+            self._num_reads.copy_(torch.as_tensor(num_reads, dtype=torch.int32).reshape(self.n_games), non_blocking=False)
+        if noise is not None:
+            noise = torch.as_tensor(noise, dtype=torch.float64).to(self.device).contiguous()
+            if noise.shape != (self.n_games, self.A):
+                raise ValueError("noise must have shape [n_games, A]")
+        self._noise = noise
+        self._ck(self.lib.dbaz_search_begin(self._h, _ptr(self._num_reads), _ptr(noise), float(coeff), self._stream()))
+
+    def step(self):
+        """One lock-step wave: backup the leaves evaluated into self.priors/self.values, then select the
+        next leaf of every tree into self.planes / self.leaf_states / self.leaf_kind."""
+        dtype, cl = self._plane_cfg
+        self._ck(self.lib.dbaz_search_step(self._h, _ptr(self.priors), _ptr(self.values), _ptr(self._planes_base),
+                                           _DTYPE_CODE[dtype], _capi.NHWC if cl else _capi.NCHW, _ptr(self.leaf_states),
+                                           _ptr(self.leaf_kind), self._stream()))
+
+    def run_search(self, num_reads, evaluator, noise=None, coeff=0.0, max_reads=None):
+        """UCT_search for all trees: `evaluator(engine)` must fill engine.priors / engine.values for the
+        leaves in engine.planes / engine.leaf_states, on the current stream, without host sync."""
+        if max_reads is None:
+            max_reads = int(num_reads) if isinstance(num_reads, int) else int(torch.as_tensor(num_reads).max())
+        self.begin(num_reads, noise, coeff)
+        # +1: an unexpanded root takes one extra simulation; +1: flush the last backup
+        for _ in range(max(max_reads, 0) + 1):
+            self.step()
+            evaluator(self)
+        self.step()
+
+    def root_visits(self):
+        out = torch.empty((self.n_games, self.A), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.dbaz_search_root_visits(self._h, _ptr(out), self._stream()))
+        return out
+
+    def root_children(self):
+        """(W float32, priors float64, sign int32, ucb float64), each [n_games, A]."""
+        n, A = self.n_games, self.A
+        W = torch.empty((n, A), dtype=torch.float32, device=self.device)
+        P = torch.empty((n, A), dtype=torch.float64, device=self.device)
+        S = torch.empty((n, A), dtype=torch.int32, device=self.device)
+        U = torch.empty((n, A), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.dbaz_search_root_children(self._h, _ptr(W), _ptr(P), _ptr(S), _ptr(U), self._stream()))
+        return W, P, S, U
+
+    def tree_stats(self):
+        """(stats int32[n, 8] = root_N, max_deepness, tree_size, terminal_count, is_expanded, is_terminal,
+        n_nodes, error; root_W float32[n]; q float32[n])."""
+        n = self.n_games
+        st = torch.empty((n, 8), dtype=torch.int32, device=self.device)
+        W = torch.empty((n,), dtype=torch.float32, device=self.device)
+        q = torch.empty((n,), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.dbaz_search_tree_stats(self._h, _ptr(st), _ptr(W), _ptr(q), self._stream()))
+        return st, W, q
+
+    def root_states(self):
+        out = torch.empty((self.n_games, 4), dtype=torch.int64, device=self.device)
+        self._ck(self.lib.dbaz_search_root_states(self._h, _ptr(out), self._stream()))
+        return out
+
+    def advance_roots(self, moves, reuse=True):
+        """init_mcts_tree (mcts.py:163-180) for every tree; moves int32[n_games], -1 = keep."""
+        moves = torch.as_tensor(moves, dtype=torch.int32).to(self.device).contiguous()
+        if moves.shape != (self.n_games,):
+            raise ValueError("moves must have shape [n_games]")
+        self._noise = None
+        self._ck(self.lib.dbaz_search_advance_roots(self._h, _ptr(moves), 1 if reuse else 0, self._stream()))
+
+    def status(self):
+        """Synchronises.  Returns dict(errors, sims, path_nodes, max_nodes_used); raises if a tree faulted."""
+        out = (C.c_int64 * 4)()
+        rc = self.lib.dbaz_search_status(self._h, out, self._stream())
+        d = {"errors": out[0], "sims": out[1], "path_nodes": out[2], "max_nodes_used": out[3]}
+        if rc != 0:
+            raise EngineError(self.lib.dbaz_last_error(self._h).decode())
+        return d
+
+
+class FakeNetEvaluator:
+    """Evaluator for parity runs: the deterministic fake net, on device."""
+
+    def __init__(self, kind=0):
+        self.kind = kind
+
+    def __call__(self, eng):
+        eng.fake_nn(eng.leaf_states, self.kind, eng.priors, eng.values)

@@ -1,0 +1,146 @@
+/*
+ * dbaz_b200.h -- C ABI of the B200-native Dots & Boxes AlphaZero self-play engine.
+ *
+ * The reference (damlobster/DotsBoxesAZ) is pure Python and has no FFI of its
+ * own; its "operator API" for the self-play hot path is the Python surface of
+ * game.py / dots_boxes/dots_boxes_game.py / mcts.py.  Each entry point below
+ * names the reference function(s) it replaces (paths relative to the reference
+ * root).  The Python binding a maintainer would add is in INTEGRATION.md and is
+ * what dotsboxesaz_b200/_capi.py implements.
+ *
+ * Conventions
+ *  - Every bulk buffer is a CALLER-OWNED DEVICE pointer (tensor.data_ptr()) of
+ *    the stated element type and shape, C-contiguous; sizes are explicit.
+ *  - `stream` is a cudaStream_t passed as an integer handle
+ *    (torch.cuda.current_stream().cuda_stream); all work is enqueued on it, no
+ *    entry point synchronises the device unless its comment says so.
+ *  - Return value: 0 = OK, non-zero = error; dbaz_last_error() gives the text.
+ *    Device-side faults (illegal move, node pool exhausted) are recorded per
+ *    game and surfaced by dbaz_search_status(); nothing throws across the ABI.
+ *  - A handle is not thread-safe; use one handle per GPU per process.
+ *  - No CPU fallback exists: without a CUDA device dbaz_engine_create() fails.
+ */
+#ifndef DBAZ_B200_H
+#define DBAZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBAZ_ABI_VERSION 1
+#define DBAZ_MAX_ACTIONS 128 /* A = 2*(L+1)*(C+1) <= 128, i.e. boards up to 7x7 boxes */
+#define DBAZ_RESULT_NONE 2   /* get_result() is None */
+
+/* Bit-packed game state, 32 bytes (dots_boxes_game.py:13, __slots__ hash/board/
+ * just_played/to_play/boxes_to_close).  Bit a of `edges` is set iff
+ * board.ravel()[a] == 255; padding cells are implied by the board size. */
+typedef struct dbaz_state {
+    uint64_t edges[2];
+    int16_t btc2[2];     /* 2 * boxes_to_close[p] (the reference stores x.5 floats) */
+    uint8_t to_play;
+    int8_t just_played;  /* -1 == None */
+    uint8_t flags;       /* engine-internal inside a tree node; 0 in user buffers */
+    uint8_t depth;       /* engine-internal */
+    int32_t parent;      /* engine-internal */
+    int16_t parent_action;
+    int16_t result;      /* engine-internal cache of get_result(), DBAZ_RESULT_NONE if None */
+} dbaz_state;
+
+typedef struct dbaz_config {
+    int32_t abi_version;   /* DBAZ_ABI_VERSION */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t board_l, board_c; /* BoxesState.BOARD_DIM (dots_boxes_game.py:23) */
+    int32_t n_games;       /* concurrent games == trees on this GPU */
+    int32_t max_nodes;     /* node-pool capacity per tree (>= sims per move + retained subtree) */
+    int32_t lut_size;      /* entries of the host-libm log table for the PUCT constant; 0 = 65536 */
+    int32_t reserved;
+    double cpuct;          /* UCTNode.CPUCT (mcts.py:44) */
+    double cpuct_base;     /* UCTNode.CPUCT_BASE (mcts.py:45) */
+} dbaz_config;
+
+typedef struct dbaz_engine dbaz_engine;
+
+/* element type codes for board-plane tensors */
+enum { DBAZ_F32 = 0, DBAZ_F16 = 1, DBAZ_BF16 = 2, DBAZ_I16 = 3 };
+/* plane layouts */
+enum { DBAZ_NCHW = 0, DBAZ_NHWC = 1 };
+
+int dbaz_abi_version(void);
+int dbaz_sizeof_state(void);
+
+/* Lifecycle.  Allocates the node pool (n_games * max_nodes * (32 + 16*A) bytes)
+ * and per-tree tables on `device`. */
+int dbaz_engine_create(const dbaz_config *cfg, dbaz_engine **out);
+void dbaz_engine_destroy(dbaz_engine *e);
+const char *dbaz_last_error(const dbaz_engine *e); /* e may be NULL: error of the last failed create */
+int dbaz_engine_info(const dbaz_engine *e, int32_t *out8); /* {L, C, A, F=3*(L+1)*(C+1), n_games, max_nodes, node_bytes, n_sms} */
+/* mcts.py:205 -- UCT_search assigns UCTNode.CPUCT/CPUCT_BASE on every call (host sync: rebuilds the log table) */
+int dbaz_engine_set_cpuct(dbaz_engine *e, double cpuct, double cpuct_base);
+
+/* ---- batched game rules over packed states (device arrays of n states) ---- */
+/* BoxesState.__init__ (dots_boxes_game.py:30-39) */
+int dbaz_game_init(dbaz_engine *e, dbaz_state *states, int64_t n, uint64_t stream);
+/* get_valid_moves (dots_boxes_game.py:44-49): out uint8[n][A], 1 = legal */
+int dbaz_game_valid_moves(dbaz_engine *e, const dbaz_state *states, uint8_t *out, int64_t n, uint64_t stream);
+/* play_ (dots_boxes_game.py:61-89): n_closed int32[n] = number of boxes closed, or -1 where the
+ * reference raises ValueError (state left untouched); closed_lc int32[n][4] (may be NULL) = the
+ * (l, c) pairs in the reference's order, -1 padded. */
+int dbaz_game_play(dbaz_engine *e, dbaz_state *states, const int32_t *moves, int32_t *n_closed,
+                   int32_t *closed_lc, int64_t n, uint64_t stream);
+/* get_result (dots_boxes_game.py:51-59): int8[n], DBAZ_RESULT_NONE for None */
+int dbaz_game_result(dbaz_engine *e, const dbaz_state *states, int8_t *out, int64_t n, uint64_t stream);
+/* get_features + nn_batch_builder (dots_boxes_game.py:96-100,148-155): planes[n][3][L+1][C+1]
+ * (or NHWC) written directly in the net's input dtype */
+int dbaz_game_features(dbaz_engine *e, const dbaz_state *states, void *planes, int32_t dtype, int32_t layout,
+                       int64_t n, uint64_t stream);
+/* Uniform random legal playouts to terminal (BASELINE config 3).  Move of game g at ply p is the
+ * floor(Philox4x32-10(key=seed, ctr=(game0+g, p)) * k / 2^32)-th legal action.  n_plies int32[n];
+ * moves uint8[n][max_plies] (may be NULL). */
+int dbaz_game_random_rollout(dbaz_engine *e, dbaz_state *states, uint64_t seed, uint64_t game0, int32_t *n_plies,
+                             uint8_t *moves, int32_t max_plies, int64_t n, uint64_t stream);
+
+/* ---- search: one tree per game, strictly sequential simulations per tree ---- */
+/* create_root_uct_node (mcts.py:156-160) for all n_games trees */
+int dbaz_search_reset_roots(dbaz_engine *e, const dbaz_state *root_states, uint64_t stream);
+/* Head of UCT_search (mcts.py:205-229).  num_reads int32[n_games] (0 = tree idle this search).
+ * noise float64[n_games][A] = Dirichlet sample already multiplied by the legal mask
+ * (mcts.py:220-223) or NULL when alpha <= 0; coeff = dirichlet[1].  Unexpanded roots get the extra
+ * initial _search() (mcts.py:207-208) before the prior mix, exactly as the reference orders it.
+ * The noise buffer must stay valid until the first dbaz_search_step() after it has returned. */
+int dbaz_search_begin(dbaz_engine *e, const int32_t *num_reads, const double *noise, double coeff, uint64_t stream);
+/* One lock-step wave = for every tree: [expand + backup of the pending leaf using priors/values]
+ * then [select_leaf + lazy child creation + feature gather] (mcts.py:105-132,184-199).
+ *   priors float32[n_games][A], values float32[n_games]: net outputs for the leaves emitted by the
+ *   PREVIOUS step (probabilities, i.e. exp(log_softmax), and tanh value; nn.py:155-160).
+ *   planes: net input for the leaves selected by THIS step; leaf_states (may be NULL): their packed
+ *   states; leaf_kind int8[n_games] (may be NULL): 0 = no leaf (tree idle/done), 1 = needs eval,
+ *   2 = terminal (net output ignored). */
+int dbaz_search_step(dbaz_engine *e, const float *priors, const float *values, void *planes, int32_t dtype,
+                     int32_t layout, dbaz_state *leaf_states, int8_t *leaf_kind, uint64_t stream);
+/* root.child_number_visits (mcts.py:244): int32[n_games][A] */
+int dbaz_search_root_visits(dbaz_engine *e, int32_t *out, uint64_t stream);
+/* Root node view: any of W float32[n][A], priors float64[n][A], sign int32[n][A], ucb float64[n][A]
+ * (children_ucb_score, mcts.py:91-99) may be NULL. */
+int dbaz_search_root_children(dbaz_engine *e, float *W, double *priors, int32_t *sign, double *ucb, uint64_t stream);
+/* Per tree int32[8]: {root_N, max_deepness, tree_size, terminal_count, is_expanded, is_terminal,
+ * n_nodes, error}; root_W float32[n]; q float32[n] (TreeRoot.get_tree_stats, mcts.py:33-36) */
+int dbaz_search_tree_stats(dbaz_engine *e, int32_t *stats8, float *root_W, float *q, uint64_t stream);
+int dbaz_search_root_states(dbaz_engine *e, dbaz_state *out, uint64_t stream);
+/* init_mcts_tree (mcts.py:163-180): moves int32[n_games], -1 = leave that tree alone.  With
+ * reuse != 0 the chosen child's subtree is kept (compacted in place), else a fresh root. */
+int dbaz_search_advance_roots(dbaz_engine *e, const int32_t *moves, int32_t reuse, uint64_t stream);
+/* Synchronises `stream`.  out int64[4] = {trees with an error flag, total sims, total path nodes,
+ * max n_nodes}.  Returns non-zero (and sets last_error) if any tree faulted. */
+int dbaz_search_status(dbaz_engine *e, int64_t *out4, uint64_t stream);
+
+/* ---- test/bench utility: deterministic stand-in for the policy/value net ----
+ * (SURVEY.md 8a KAT definition; kind 0 hash-seeded, kind 1 uniform prior) over leaf_states[n]. */
+int dbaz_fake_nn(dbaz_engine *e, const dbaz_state *leaf_states, float *priors, float *values, int32_t kind,
+                 int64_t n, uint64_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBAZ_B200_H */
