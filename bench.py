@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS simulations/sec of the self-play hot path (BASELINE.json metric).
+
+Own arm (default):   python bench.py --gpus N --steps K --warmup W
+Reference arm:       python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one UCT_search (`--sims` simulations per tree, default 800) for every one of the
+`--games` concurrent games of a GPU (default 4096, 3x3 boxes = BASELINE configs[1]) from synthetic
+root positions, with Dirichlet root noise (0.8, 0.25) and the reference's SimpleNN (random-init,
+seed 0) as leaf evaluator.  One process per GPU; games are sharded by index, there is no data-path
+collective (weak scaling).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mcts_sims_per_sec"
+UNIT = "sims/s"
+NOISE = (0.8, 0.25)
+MAX_ROOT_PLIES = 12
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--board", default="3x3")
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--sims", type=int, default=800, help="simulations per move")
+    ap.add_argument("--net", default="simple", choices=["simple", "resnet", "fake"])
+    ap.add_argument("--net-dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--graph-waves", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-workers", type=int, default=0, help="processes for the CPU baseline (0 = min(cores-1, 64))")
+    ap.add_argument("--cpu-positions", type=int, default=2, help="searches per worker in the bounded CPU sample")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return ("%s boxes, %d concurrent games/GPU, %d sims/move, one UCT_search per step from synthetic roots "
+            "(0-%d random plies), Dirichlet%s, net=%s" % (args.board, args.games, args.sims, MAX_ROOT_PLIES, NOISE, args.net))
+
+
+# ------------------------------------------------------------------ CPU side
+def cpu_workers(args):
+    cores = os.cpu_count() or 1
+    return args.cpu_workers if args.cpu_workers > 0 else max(1, min(cores - 1, 64))
+
+
+def run_cpu_sample(args, pool, workers, n_pos, seed0):
+    """Every worker runs `n_pos` searches of the bench workload on the Python restatement of the
+    reference (oracle/py_port.py: asyncio MCTS + age-triggered batching proxy + SimpleNN on CPU,
+    1 torch thread per process -- the reference's own process layout, self_play.py:291-306)."""
+    from oracle import py_port
+    L, C = (int(x) for x in args.board.split("x"))
+    net = "simple" if args.net != "fake" else "fake"
+    jobs = [((L, C), args.sims, n_pos, seed0 + w, net, MAX_ROOT_PLIES) for w in range(workers)]
+    t0 = time.time()
+    res = pool.map(py_port.worker_search, jobs)
+    wall = time.time() - t0
+    sims = sum(r[0] for r in res)
+    return sims, wall
+
+
+def cpu_baseline(args):
+    import multiprocessing as mp
+    workers = cpu_workers(args)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        run_cpu_sample(args, pool, workers, 1, 1000)  # warm-up: imports, torch init
+        sims, wall = run_cpu_sample(args, pool, workers, args.cpu_positions, 2000)
+    return {"value": sims / wall, "unit": UNIT, "cores": workers, "kind": "port",
+            "sample": "%d processes x %d UCT_search(%d sims) of the bench workload on oracle/py_port.py "
+                      "(Python/NumPy restatement of the reference incl. its 48-batch/50 ms proxy and 400k LRU, SimpleNN fp32 "
+                      "on CPU, 1 torch thread per process); %d sims in %.1f s wall"
+                      % (workers, args.cpu_positions, args.sims, sims, wall),
+            "host_cores": os.cpu_count()}
+
+
+def c_oracle_rate(args):
+    """Single-core rate of the C oracle (fake net, tree-only) -- context for the port's number."""
+    from oracle import oracle
+    L, C = (int(x) for x in args.board.split("x"))
+    t0 = time.time()
+    _, _, sims, _ = oracle.selfplay_argmax(L, C, args.sims)
+    return sims / (time.time() - t0)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = cpu_workers(args)
+    ctx = mp.get_context("spawn")
+    per_step = 1
+    with ctx.Pool(workers) as pool:
+        for w in range(max(args.warmup, 1)):
+            run_cpu_sample(args, pool, workers, per_step, 100 + 1000 * w)
+        tot_sims, tot_wall = 0, 0.0
+        for k in range(args.steps):
+            s, wl = run_cpu_sample(args, pool, workers, per_step, 50000 + 1000 * k)
+            tot_sims += s
+            tot_wall += wl
+    value = tot_sims / tot_wall
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * tot_wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 PUCT over f32/i32 node stats (NumPy); net fp32 on CPU", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": workload_name(args), "board": args.board, "sims_per_move": args.sims,
+                       "step": "each of %d processes runs %d UCT_search(%d) on a synthetic root" % (workers, per_step, args.sims)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                             "sample": "oracle/py_port.py (Python/NumPy restatement of the reference; the reference itself is "
+                                       "Python and /root/reference does not exist on the GPU box), %d processes, 1 torch "
+                                       "thread each" % workers, "host_cores": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU side
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def synthetic_roots(eng, torch, seed):
+    """Random legal positions 0..MAX_ROOT_PLIES plies deep, built on the device with the engine's own
+    rules kernels (never terminal on 3x3/5x5 at this depth)."""
+    g = torch.Generator(device=eng.device)
+    g.manual_seed(seed)
+    n = eng.n_games
+    st = eng.new_states(n)
+    depth = torch.randint(0, MAX_ROOT_PLIES + 1, (n,), generator=g, device=eng.device)
+    for ply in range(MAX_ROOT_PLIES):
+        legal = eng.valid_moves(st).float()
+        mv = torch.multinomial(legal + 1e-9, 1, generator=g).reshape(-1).int()
+        mv = torch.where((depth > ply) & (legal.sum(1) > 0), mv, torch.full_like(mv, -1))
+        eng.play(st, mv)
+    return st
+
+
+def host_noise(rs, valid_np, alpha):
+    import numpy as np
+    A = valid_np.shape[1]
+    return rs.dirichlet(np.ones(A) * alpha, size=valid_np.shape[0]) * valid_np  # mcts.py:220-223
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N=1 only), before CUDA is initialised, so the two never overlap
+    cpu = None
+    c_rate = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args)
+        c_rate = c_oracle_rate(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dotsboxesaz_b200 import engine
+    from dotsboxesaz_b200.nn import DeviceEvaluator, ResNetZero, resnet_zero_parameters
+    from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
+    from dotsboxesaz_b200.utils.utils import DotDict
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    L, C = (int(x) for x in args.board.split("x"))
+    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.sims + 8, device=dev)
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.net_dtype]
+    if args.net == "fake":
+        ev = engine.FakeNetEvaluator(0)
+    else:
+        torch.manual_seed(0)
+        model = SimpleNN(board=(L, C)) if args.net == "simple" else ResNetZero(
+            DotDict({"nn": {"model_parameters": resnet_zero_parameters((L, C))}}))
+        ev = DeviceEvaluator(model, eng, dtype=dt, channels_last=True)
+
+    roots = synthetic_roots(eng, torch, seed=1234 + rank)
+    valid_np = eng.valid_moves(roots).cpu().numpy()
+    rs = np.random.RandomState(99 + rank)
+    noise_dev = torch.from_numpy(host_noise(rs, valid_np, NOISE[0])).to(dev)
+    visits = torch.empty((args.games, eng.A), dtype=torch.int32, device=dev)
+
+    def step_resident():
+        eng.reset_roots(roots)
+        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves)
+        visits.copy_(eng.root_visits())
+
+    # host buffers of the end-to-end arm (pinned)
+    roots_host = roots.cpu().pin_memory()
+    noise_host = torch.empty((args.games, eng.A), dtype=torch.float64).pin_memory()
+    visits_host = torch.empty((args.games, eng.A), dtype=torch.int32).pin_memory()
+    roots_in = torch.empty_like(roots)
+
+    def step_e2e():
+        noise_host.copy_(torch.from_numpy(host_noise(rs, valid_np, NOISE[0])))  # host-side RNG, as the reference
+        roots_in.copy_(roots_host, non_blocking=True)
+        noise_dev.copy_(noise_host, non_blocking=True)
+        eng.reset_roots(roots_in)
+        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves)
+        visits_host.copy_(eng.root_visits(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(visits_host[0].sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1), (time.time() - t0) * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1])
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.n_launches
+    ms, _wall = timed(step_resident, args.steps)
+    launches = eng.n_launches - l0
+    st = eng.status()  # also checks that no tree faulted
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    sims_per_step = args.games * args.sims * world
+    value = sims_per_step * args.steps / (ms / 1e3)
+    e2e_value = sims_per_step * args.steps / (max(ms_e2e, wall_e2e) / 1e3)
+
+    # ---- roofline of the dominant kernel of MY code (k_search_step), timed live with CUDA events on
+    # the launching stream, one event pair per launch, with the real evaluator between launches
+    P = st["path_nodes"] / max(1, st["sims"])
+    f_term = st["terminal_leaves"] / max(1, st["sims"])
+    A, F = eng.A, eng.F
+    plane_b = 4 if (args.net == "fake" or args.net_dtype == "fp32") else 2
+    bytes_per_sim = (P - 1) * (13 * A + 24) + 36 + 24 * P + (1 - f_term) * (F * plane_b + 17 * A + 4)
+    roof = None
+    if rank == 0:
+        eng.reset_roots(roots)
+        eng.begin(args.sims, noise_dev, NOISE[1])
+        evs = []
+        for w in range(args.sims + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); eng.step(); b.record()
+            ev(eng)
+            if 16 <= w < args.sims:
+                evs.append((a, b))
+        eng.step()
+        torch.cuda.synchronize()
+        k_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_per_sim * args.games / (k_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_search_step_dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "k_search_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
+                "kernel_us": k_ms * 1e3, "algorithmic_bytes_per_sim": bytes_per_sim, "mean_path_nodes": P,
+                "terminal_leaf_frac": f_term, "share_of_step": k_ms * (args.sims + 2) / (ms / args.steps)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 PUCT over f32/i32 node stats; net %s" % (args.net_dtype if args.net != "fake" else "none (fake)"),
+                "data": "synthetic",
+                "config": {"workload": workload_name(args), "board": args.board, "games_per_gpu": args.games,
+                           "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "parallelism": "games sharded by index x%d, no collective" % world,
+                           "l2": "inputs larger than L2: node pool touched per step %.2f GB/GPU vs 126 MB L2" % (
+                               args.games * (args.sims + 1) * eng.node_bytes / 1e9),
+                           "graph_waves": args.graph_waves},
+                "games_per_hour_equiv": None,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": max(ms_e2e, wall_e2e) / args.steps,
+                        "h2d_bytes_per_step": int(roots_host.numel() * 8 + noise_host.numel() * 8),
+                        "d2h_bytes_per_step": int(visits_host.numel() * 4),
+                        "api": "Engine.reset_roots(host roots) + Engine.run_search(host Dirichlet noise) + root_visits -> host"},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+        if c_rate is not None:
+            line["cpu_c_oracle_1core_sims_per_sec"] = c_rate
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,7 +144,7 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
               alloc((void**)&ta.root_prior, (size_t)ta.n_trees * A * sizeof(double), "root priors") &&
               alloc((void**)&ta.path, (size_t)ta.n_trees * PATH_CAP * sizeof(uint32_t), "paths") &&
               alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double), "log table") &&
-              alloc((void**)&e->d_status, 4 * sizeof(unsigned long long), "status");
+              alloc((void**)&e->d_status, 8 * sizeof(unsigned long long), "status");
     if (!ok) { dbaz_engine_destroy(e); return 1; }
     if (upload_lut(e)) { g_create_err = e->err; dbaz_engine_destroy(e); return 1; }
 
@@ -327,16 +327,16 @@ int dbaz_search_advance_roots(dbaz_engine* e, const int32_t* moves, int32_t reus
     return launch_ok(e, "k_advance_roots");
 }
 
-int dbaz_search_status(dbaz_engine* e, int64_t* out4, uint64_t stream) {
+int dbaz_search_status(dbaz_engine* e, int64_t* out8, uint64_t stream) {
     if (!e) return 1;
     DeviceGuard guard(e->cfg.device);
-    DBAZ_CK(e, cudaMemsetAsync(e->d_status, 0, 4 * sizeof(unsigned long long), S(stream)));
+    DBAZ_CK(e, cudaMemsetAsync(e->d_status, 0, 8 * sizeof(unsigned long long), S(stream)));
     k_status<<<blocks_for(e->ta.n_trees, 128), 128, 0, S(stream)>>>(e->ta, e->d_status);
     if (launch_ok(e, "k_status")) return 1;
-    unsigned long long h[4];
+    unsigned long long h[8];
     DBAZ_CK(e, cudaMemcpyAsync(h, e->d_status, sizeof h, cudaMemcpyDeviceToHost, S(stream)));
     DBAZ_CK(e, cudaStreamSynchronize(S(stream)));
-    if (out4) for (int i = 0; i < 4; ++i) out4[i] = (int64_t)h[i];
+    if (out8) for (int i = 0; i < 8; ++i) out8[i] = (int64_t)h[i];
     if (h[0]) {
         char buf[160];
         std::snprintf(buf, sizeof buf, "%llu tree(s) faulted: node pool exhausted (max_nodes=%d) or illegal re-root move",

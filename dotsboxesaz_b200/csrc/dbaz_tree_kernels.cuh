@@ -43,7 +43,7 @@ struct __align__(64) TreeRec {
     int32_t deepness_correction;
     int32_t terminal_count;
     int32_t tree_size;
-    int32_t root_sign;
+    int32_t total_term;   // terminal leaves since reset (instrumentation)
     unsigned long long total_sims, total_path;
 };
 static_assert(sizeof(TreeRec) == 64, "TreeRec must be 64 bytes");
@@ -278,7 +278,7 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
     if (lane == 0) {
         T.terminal_count += terminal ? 1 : 0;
         T.max_deepness = max(T.max_deepness, (int)lh.depth);
-        if (T.leaf == 0) T.root_sign = (lh.to_play == (uint8_t)lh.just_played) ? 1 : -1;
+        T.total_term += terminal ? 1 : 0;
         T.leaf = -1;
         T.total_sims += 1;
         T.total_path += plen;
@@ -462,7 +462,7 @@ __global__ void k_reset_roots(Board b, TreeArgs ta, const dbaz_state* __restrict
     store_hdr(node_ptr(ta, t, 0), s);
     TreeRec T;
     T.n_nodes = 1; T.root_N = 0; T.root_W = 0.0f; T.sims_left = 0; T.leaf = -1; T.path_len = 0; T.flags = 0;
-    T.max_deepness = 0; T.deepness_correction = 0; T.terminal_count = 0; T.tree_size = 0; T.root_sign = 0;
+    T.max_deepness = 0; T.deepness_correction = 0; T.terminal_count = 0; T.tree_size = 0; T.total_term = 0;
     T.total_sims = 0; T.total_path = 0;
     ta.trees[t] = T;
 }
@@ -596,7 +596,7 @@ k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reu
         }
     }
     if (tid == 0) {
-        T.root_N = 0; T.root_W = 0.0f; T.root_sign = 0; T.leaf = -1; T.path_len = 0; T.sims_left = 0;
+        T.root_N = 0; T.root_W = 0.0f; T.leaf = -1; T.path_len = 0; T.sims_left = 0;
         T.max_deepness = 0; T.terminal_count = 0;
         T.flags &= ~(TF_PRIOR_SET | TF_PRIOR_F64 | TF_PREP_PENDING);
         ta.trees[t] = T;
@@ -669,7 +669,7 @@ __global__ void k_root_states(TreeArgs ta, dbaz_state* __restrict__ out) {
     out[t] = h;
 }
 
-// {errored trees, total sims, total path nodes, max n_nodes} by atomics into out4 (zeroed by the host)
+// {errored trees, total sims, total path nodes, max n_nodes, terminal leaves} by atomics (zeroed by the host)
 __global__ void k_status(TreeArgs ta, unsigned long long* __restrict__ out4) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ta.n_trees) return;
@@ -678,6 +678,7 @@ __global__ void k_status(TreeArgs ta, unsigned long long* __restrict__ out4) {
     atomicAdd(&out4[1], T.total_sims);
     atomicAdd(&out4[2], T.total_path);
     atomicMax(&out4[3], (unsigned long long)T.n_nodes);
+    atomicAdd(&out4[4], (unsigned long long)T.total_term);
 }
 
 }  // namespace dbaz

@@ -59,6 +59,10 @@ class Engine:
         self._plane_cfg = None
         self._noise = None  # keeps the caller's noise buffer alive while the engine may read it
         self._num_reads = torch.zeros((n_games,), dtype=torch.int32, device=self.device)
+        self._idle_reads = torch.full((n_games,), -1, dtype=torch.int32, device=self.device)
+        self._noise_buf = None
+        self._graphs = {}
+        self.n_launches = 0  # engine kernels enqueued (graph replays count the kernels they contain)
         self.set_planes(torch.float32, channels_last=False)
 
     # ------------------------------------------------------------ plumbing
@@ -76,7 +80,8 @@ class Engine:
     def _stream(self):
         return C.c_uint64(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _ck(self, rc):
+    def _ck(self, rc, launches=1):
+        self.n_launches += launches
         if rc != 0:
             raise EngineError(self.lib.dbaz_last_error(self._h).decode())
 
@@ -218,17 +223,60 @@ class Engine:
                                            _DTYPE_CODE[dtype], _capi.NHWC if cl else _capi.NCHW, _ptr(self.leaf_states),
                                            _ptr(self.leaf_kind), self._stream()))
 
-    def run_search(self, num_reads, evaluator, noise=None, coeff=0.0, max_reads=None):
-        """UCT_search for all trees: `evaluator(engine)` must fill engine.priors / engine.values for the
-        leaves in engine.planes / engine.leaf_states, on the current stream, without host sync."""
+    def run_search(self, num_reads, evaluator, noise=None, coeff=0.0, max_reads=None, graph_waves=0):
+        """UCT_search for all trees.  `evaluator(engine)` must fill engine.priors / engine.values for the
+        leaves in engine.planes / engine.leaf_states, on the current stream, without host sync.
+
+        graph_waves > 0: `graph_waves` consecutive [step kernel -> evaluator] waves are captured once in a
+        CUDA graph and replayed, so the 800-wave inner loop costs one launch per `graph_waves` waves.
+        Surplus waves at the end of the last replay are no-ops for trees that have finished."""
         if max_reads is None:
             max_reads = int(num_reads) if isinstance(num_reads, int) else int(torch.as_tensor(num_reads).max())
-        self.begin(num_reads, noise, coeff)
-        # +1: an unexpanded root takes one extra simulation; +1: flush the last backup
-        for _ in range(max(max_reads, 0) + 1):
-            self.step()
-            evaluator(self)
-        self.step()
+        waves = max(max_reads, 0) + 1  # +1: an unexpanded root takes one extra simulation
+        if graph_waves > 0:
+            if noise is not None:  # a stable address for the captured step kernel
+                if self._noise_buf is None:
+                    self._noise_buf = torch.zeros((self.n_games, self.A), dtype=torch.float64, device=self.device)
+                self._noise_buf.copy_(torch.as_tensor(noise, dtype=torch.float64).reshape(self.n_games, self.A))
+                noise = self._noise_buf
+            key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg)
+            if key not in self._graphs:
+                self._graphs[key] = self._capture(evaluator, graph_waves, noise, coeff)
+            self.begin(num_reads, noise, coeff)
+            g = self._graphs[key]
+            per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
+            for _ in range((waves + graph_waves - 1) // graph_waves):
+                g.replay()
+                self.n_launches += graph_waves * per_wave
+        else:
+            self.begin(num_reads, noise, coeff)
+            for _ in range(waves):
+                self.step()
+                evaluator(self)
+        self.step()  # flush the last backup
+
+    def _capture(self, evaluator, graph_waves, noise, coeff):
+        # warm up the evaluator alone (allocator, cuDNN heuristics); no leaf is pending between searches,
+        # so overwriting priors/values here is harmless
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                evaluator(self)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        # the captured step kernels carry the noise pointer / coeff of begin(); bind them first
+        self._noise = noise
+        self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), _ptr(noise), float(coeff), self._stream())
+        g = torch.cuda.CUDAGraph()
+        n0 = self.n_launches
+        with torch.cuda.graph(g):
+            for _ in range(graph_waves):
+                self.step()
+                evaluator(self)
+        self.n_launches = n0  # capture enqueues nothing
+        return g
 
     def root_visits(self):
         out = torch.empty((self.n_games, self.A), dtype=torch.int32, device=self.device)
@@ -270,9 +318,9 @@ class Engine:
 
     def status(self):
         """Synchronises.  Returns dict(errors, sims, path_nodes, max_nodes_used); raises if a tree faulted."""
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 8)()
         rc = self.lib.dbaz_search_status(self._h, out, self._stream())
-        d = {"errors": out[0], "sims": out[1], "path_nodes": out[2], "max_nodes_used": out[3]}
+        d = {"errors": out[0], "sims": out[1], "path_nodes": out[2], "max_nodes_used": out[3], "terminal_leaves": out[4]}
         if rc != 0:
             raise EngineError(self.lib.dbaz_last_error(self._h).decode())
         return d
@@ -280,6 +328,8 @@ class Engine:
 
 class FakeNetEvaluator:
     """Evaluator for parity runs: the deterministic fake net, on device."""
+
+    engine_launches = 1  # one k_fake_nn per wave
 
     def __init__(self, kind=0):
         self.kind = kind

@@ -1,0 +1,238 @@
+"""Policy/value nets and the inference wrapper (reference: nn.py, dots_boxes/dots_boxes_nn.py).
+
+The nets are the only dense contraction of the path and stay plain PyTorch (cuDNN / cuBLAS
+on the tensor cores); module and parameter names equal the reference's so that its
+`model_gen{g}.pt` checkpoints (`{'last_batch_idx', 'model_dict', 'optimizer_dict'}`,
+nn.py:293-295) load unchanged.  `DeviceEvaluator` is the engine-facing replacement of
+AsyncBatchedProxy + NeuralNetWrapper.predict_sync (utils/proxies.py:34-72, nn.py:155-160):
+it reads the leaf planes the select kernel wrote, runs the net in eval mode, and writes
+exp(log p) and v into the engine's float32 buffers -- all on the current stream, with no
+host round trip, so Engine.run_search can capture whole waves in a CUDA graph.
+"""
+import asyncio
+import logging
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+logger = logging.getLogger(__name__)
+
+
+def _conv(in_ch, out_ch, k, groups=1, padding=True):
+    # nn.py:61-71: odd kernels use symmetric padding, even kernels pad right/bottom
+    if k % 2 == 1:
+        return nn.Conv2d(in_ch, out_ch, k, padding=(k - 1) // 2 if padding else 0, groups=groups)
+    conv = nn.Conv2d(in_ch, out_ch, k, padding=0, groups=groups)
+    if not padding:
+        return conv
+    return nn.Sequential(nn.ConstantPad2d((0, k // 2, 0, k // 2), 0.0), conv)
+
+
+class ResBlock(nn.Module):
+    """nn.py:33-58"""
+
+    def __init__(self, nb_channels, kernel_size, n_groups, inner_channels):
+        super().__init__()
+        inner = inner_channels if inner_channels else nb_channels
+        self.inner_conv = None
+        if inner_channels:
+            self.inner_conv = _conv(inner, inner, kernel_size, n_groups)
+            self.inner_bn = nn.BatchNorm2d(inner)
+        self.conv1 = _conv(nb_channels, inner, kernel_size, n_groups)
+        self.bn1 = nn.BatchNorm2d(inner)
+        self.conv2 = _conv(inner, nb_channels, kernel_size, n_groups)
+        self.bn2 = nn.BatchNorm2d(nb_channels)
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        if self.inner_conv is not None:
+            y = F.relu(self.inner_bn(self.inner_conv(y)))
+        y = self.bn2(self.conv2(y))
+        return F.relu(y + x)
+
+
+class ResNet(nn.Module):
+    """nn.py:16-30"""
+
+    def __init__(self, in_channels, nb_channels, kernel_size, nb_blocks, n_groups=1, inner_channels=None, pad_layer0=True):
+        super().__init__()
+        self.conv0 = _conv(in_channels, nb_channels, 3, 1, pad_layer0)
+        self.bn0 = nn.BatchNorm2d(nb_channels)
+        self.resblocks = nn.Sequential(*(ResBlock(nb_channels, kernel_size, n_groups, inner_channels) for _ in range(nb_blocks)))
+
+    def forward(self, x):
+        return self.resblocks(F.relu(self.bn0(self.conv0(x))))
+
+
+class PolicyHead(nn.Module):
+    """nn.py:74-87"""
+
+    def __init__(self, in_channels, inner_channels, fc_in, nb_actions):
+        super().__init__()
+        self.conv0 = nn.Conv2d(in_channels, inner_channels, kernel_size=(1, 1))
+        self.bn0 = nn.BatchNorm2d(inner_channels)
+        self.fc = nn.Linear(fc_in, nb_actions)
+
+    def forward(self, x):
+        x = F.relu(self.bn0(self.conv0(x)))
+        return F.log_softmax(self.fc(x.reshape(x.size(0), -1)), dim=1)
+
+
+class ValueHead(nn.Module):
+    """nn.py:90-105"""
+
+    def __init__(self, in_channels, inner_channels, fc_in, fc_inner):
+        super().__init__()
+        self.conv0 = nn.Conv2d(in_channels, inner_channels, kernel_size=(1, 1))
+        self.bn0 = nn.BatchNorm2d(inner_channels)
+        self.fc0 = nn.Linear(fc_in, fc_inner)
+        self.fc1 = nn.Linear(fc_inner, 1)
+
+    def forward(self, x):
+        x = F.relu(self.bn0(self.conv0(x)))
+        x = F.relu(self.fc0(x.reshape(x.size(0), -1)))
+        return torch.tanh(self.fc1(x))
+
+
+def _load_parameters(model, generation, to_device=None):
+    fn = model.params.nn.chkpts_filename.format(generation)
+    logger.info("Model loaded from: %s", fn)
+    model.load_state_dict(torch.load(fn, map_location="cpu")["model_dict"])
+    model.to(to_device)
+
+
+class ResNetZero(nn.Module):
+    """nn.py:108-129.  `params.nn.model_parameters` = {resnet, value_head, policy_head} kwargs."""
+
+    def __init__(self, params):
+        super().__init__()
+        self.params = params
+        mp = params.nn.model_parameters
+        self.bn_input = nn.BatchNorm2d(mp.resnet.in_channels)
+        self.resnet = ResNet(**mp.resnet)
+        self.value_head = ValueHead(**mp.value_head)
+        self.policy_head = PolicyHead(**mp.policy_head)
+
+    def forward(self, x):
+        x = self.resnet(self.bn_input(x))
+        return self.policy_head(x), self.value_head(x)
+
+    def load_parameters(self, generation, to_device=None):
+        _load_parameters(self, generation, to_device)
+
+
+def resnet_zero_parameters(board=(3, 3), nb_channels=64, nb_blocks=20, head_channels=16, fc_inner=8):
+    """model_parameters for a board of L x C boxes; (3, 3) reproduces configuration.py:133-155."""
+    rows, cols = board[0] + 1, board[1] + 1
+    fc_in = head_channels * rows * cols
+    return {"resnet": {"pad_layer0": True, "in_channels": 3, "nb_channels": nb_channels, "inner_channels": None,
+                       "kernel_size": 3, "nb_blocks": nb_blocks, "n_groups": 1},
+            "policy_head": {"in_channels": nb_channels, "inner_channels": head_channels, "fc_in": fc_in,
+                            "nb_actions": 2 * rows * cols},
+            "value_head": {"in_channels": nb_channels, "inner_channels": head_channels, "fc_in": fc_in, "fc_inner": fc_inner}}
+
+
+class AlphaZeroLoss(nn.Module):
+    """nn.py:131-138"""
+
+    def forward(self, p, v, pi, z):
+        loss_v = (z - v).pow(2).mean()
+        loss_pi = -(pi * p).sum(1).mean()
+        return loss_v + loss_pi, (loss_pi.item(), loss_v.item())
+
+
+class NeuralNetWrapper:
+    """nn.py:145-173: the host-facing predict API (numpy in, numpy out).  Training lives in train.py."""
+
+    def __init__(self, model, params):
+        self.params = params
+        self.device = torch.device(params.nn.pytorch_device if torch.cuda.is_available() else "cpu")
+        self.model = model.to(self.device) if model is not None else None
+
+    def set_model(self, model):
+        self.model = model.to(self.device)
+
+    @torch.no_grad()
+    def predict_sync(self, X):
+        self.model.train(False)
+        x = torch.as_tensor(np.asarray(X), dtype=torch.float32, device=self.device)
+        p, v = self.model(x)
+        return torch.exp(p).cpu().numpy(), v.cpu().numpy()
+
+    async def predict(self, X):
+        return await asyncio.get_event_loop().run_in_executor(None, self.predict_sync, X)
+
+    async def predict_from_game(self, game_state):
+        return await self.predict([game_state.get_features()])
+
+    async def __call__(self, X):
+        return await self.predict(X)
+
+
+class GenerationLrScheduler:
+    """nn.py:276-290"""
+
+    def __init__(self, schedule):
+        assert schedule is not None
+        self.schedule = schedule
+
+    def __call__(self, generation):
+        lr = None
+        for g in range(generation + 1):
+            lr = self.schedule.get(g, lr)
+        assert lr is not None
+        return lr
+
+    def __repr__(self):
+        return f"GenerationLrScheduler({self.schedule})"
+
+
+def save_checkpoint(filename, model, optimizer, last_batch_idx):
+    torch.save({"last_batch_idx": last_batch_idx, "model_dict": model.state_dict(), "optimizer_dict": optimizer.state_dict()},
+               filename)
+
+
+def load_checkpoint(filename, model, optimizer, to_device):
+    if not os.path.isfile(filename):
+        raise ValueError(f"=> no checkpoint found at '{filename}'")
+    ck = torch.load(filename, map_location="cpu")
+    model.load_state_dict(ck["model_dict"])
+    optimizer.load_state_dict(ck["optimizer_dict"])
+    model.to(to_device)
+    for state in optimizer.state.values():
+        for k, v in state.items():
+            if isinstance(v, torch.Tensor):
+                state[k] = v.to(to_device)
+    return ck["last_batch_idx"]
+
+
+# ----------------------------------------------------------------- engine side
+class DeviceEvaluator:
+    """Leaf evaluation for the lock-step search: engine.planes -> net -> engine.priors / engine.values.
+
+    dtype: compute dtype of the net (torch.bfloat16 default; float32 reproduces the reference's
+    arithmetic type).  The select kernel writes the planes directly in this dtype and, with
+    channels_last, directly in NHWC, so no cast / permute kernels run before the first conv.
+    """
+
+    def __init__(self, model, engine, dtype=torch.bfloat16, channels_last=True):
+        self.engine = engine
+        self.dtype = dtype
+        self.model = model.to(engine.device).train(False)
+        if dtype != torch.float32:
+            self.model = self.model.to(dtype)
+        if channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)
+        for p in self.model.parameters():
+            p.requires_grad_(False)
+        engine.set_planes(dtype, channels_last)
+
+    @torch.no_grad()
+    def __call__(self, eng):
+        """Capturable: fixed input/output addresses, no host sync (Engine.run_search(graph_waves=...))."""
+        logp, v = self.model(eng.planes)
+        torch.exp(logp.float(), out=eng.priors)  # nn.py:159: probabilities, float32
+        eng.values.copy_(v.reshape(-1))

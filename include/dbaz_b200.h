@@ -131,9 +131,10 @@ int dbaz_search_root_states(dbaz_engine *e, dbaz_state *out, uint64_t stream);
 /* init_mcts_tree (mcts.py:163-180): moves int32[n_games], -1 = leave that tree alone.  With
  * reuse != 0 the chosen child's subtree is kept (compacted in place), else a fresh root. */
 int dbaz_search_advance_roots(dbaz_engine *e, const int32_t *moves, int32_t reuse, uint64_t stream);
-/* Synchronises `stream`.  out int64[4] = {trees with an error flag, total sims, total path nodes,
- * max n_nodes}.  Returns non-zero (and sets last_error) if any tree faulted. */
-int dbaz_search_status(dbaz_engine *e, int64_t *out4, uint64_t stream);
+/* Synchronises `stream`.  out int64[8] = {trees with an error flag, total sims, total path nodes,
+ * max n_nodes, terminal leaves, 0, 0, 0} (totals since reset_roots).  Returns non-zero (and sets
+ * last_error) if any tree faulted. */
+int dbaz_search_status(dbaz_engine *e, int64_t *out8, uint64_t stream);
 
 /* ---- test/bench utility: deterministic stand-in for the policy/value net ----
  * (SURVEY.md 8a KAT definition; kind 0 hash-seeded, kind 1 uniform prior) over leaf_states[n]. */
