@@ -288,6 +288,13 @@ int dbaz_search_step(dbaz_engine* e, const float* priors, const float* values, v
     return launch_ok(e, "k_search_step");
 }
 
+int dbaz_search_stop(dbaz_engine* e, uint64_t stream) {
+    if (!e) return 1;
+    DeviceGuard guard(e->cfg.device);
+    k_search_stop<<<blocks_for(e->ta.n_trees, 128), 128, 0, S(stream)>>>(e->ta);
+    return launch_ok(e, "k_search_stop");
+}
+
 int dbaz_search_root_visits(dbaz_engine* e, int32_t* out, uint64_t stream) {
     if (!e || !out) return 1;
     DeviceGuard guard(e->cfg.device);

@@ -383,7 +383,13 @@ k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, cons
     TreeRec T = ta.trees[t];
     const int nr = num_reads[t];
     T.leaf = -1;
-    if (nr < 0) {
+    if (nr == -2) {
+        // only the initial _search() of an unexpanded root (mcts.py:207-208), no prior mix: lets a host
+        // caller draw its Dirichlet noise AFTER the root evaluation, in the reference's RNG order
+        dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
+        T.sims_left = (rh.flags & NF_EXPANDED) ? 0 : 1;
+        T.flags &= ~TF_PREP_PENDING;
+    } else if (nr < 0) {
         T.sims_left = 0;
         T.flags &= ~TF_PREP_PENDING;
     } else {
@@ -446,6 +452,14 @@ k_search_step(Board b, TreeArgs ta, const float* __restrict__ priors, const floa
         ta.trees[t] = T;
         if (leaf_kind) leaf_kind[t] = (int8_t)kind;
     }
+}
+
+// UCT_search's time limit (mcts.py:232-233): launch no further simulations; pending leaves still back up
+__global__ void k_search_stop(TreeArgs ta) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ta.n_trees) return;
+    ta.trees[t].sims_left = 0;
+    ta.trees[t].flags &= ~TF_PREP_PENDING;
 }
 
 // create_root_uct_node for every tree

@@ -223,6 +223,11 @@ class Engine:
                                            _DTYPE_CODE[dtype], _capi.NHWC if cl else _capi.NCHW, _ptr(self.leaf_states),
                                            _ptr(self.leaf_kind), self._stream()))
 
+    def step_flush(self):
+        """Stop launching simulations (UCT_search's time limit) and back up the pending leaves."""
+        self._ck(self.lib.dbaz_search_stop(self._h, self._stream()))
+        self.step()
+
     def run_search(self, num_reads, evaluator, noise=None, coeff=0.0, max_reads=None, graph_waves=0):
         """UCT_search for all trees.  `evaluator(engine)` must fill engine.priors / engine.values for the
         leaves in engine.planes / engine.leaf_states, on the current stream, without host sync.

@@ -1,0 +1,298 @@
+"""Self-play drivers (reference: self_play.py).
+
+SelfPlay         drop-in for self_play.py:19-156: one game at a time through the mcts drop-in and any
+                 `async nn(game_state)`; same temperature / np.random.choice protocol, same played_games
+                 layout and the same get_datasets() DataFrame.
+BatchedSelfPlay  the B200 path: `n_games` games in lock-step on one Engine, leaf evaluation by a
+                 device-resident evaluator, per-game legacy RNG streams on the host so that a game
+                 played with seed s is move-for-move the game the reference plays after
+                 np.random.seed(s).
+generate_games   self_play.py:291-306 re-targeted: games are sharded by index over the ranks of
+                 torch.distributed (one process per GPU) instead of an mp.Pool; the sample rows are
+                 gathered to rank 0 (the reference appends to an HDF file under a lock).
+"""
+import logging
+import math
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import mcts
+from ._capi import RESULT_NONE, STATE_DTYPE
+from .dots_boxes.dots_boxes_game import BoxesState
+
+logger = logging.getLogger(__name__)
+
+
+def _apply_temperature(visit_counts, temperature):
+    # self_play.py:32-33 (float64)
+    probs = (visit_counts / visit_counts.max()) ** (1 / temperature)
+    return probs / probs.sum()
+
+
+def _n_searches(n_valid, num_read):
+    return min(4 * math.factorial(n_valid), num_read)  # self_play.py:64-65
+
+
+def _dataset(rows, generation, with_features):
+    """The DataFrame of self_play.py:95-156 from row dicts (same columns, dtypes and MultiIndex)."""
+    n = len(rows)
+    players = np.asarray([r["player"] for r in rows], dtype=np.int8)
+    if isinstance(generation, (list, tuple)):
+        gen = np.zeros(n, dtype=np.int16)
+        gen[players == 0] = generation[0]
+        gen[players == 1] = generation[1]
+    else:
+        gen = np.asarray([generation] * n, dtype=np.int16)
+    cols = {"generation": gen, "game_idx": np.asarray([r["game_idx"] for r in rows], dtype=np.int16),
+            "move_idx": np.asarray([r["move_idx"] for r in rows], dtype=np.int16),
+            "move": np.asarray([-1 if r["move"] is None else r["move"] for r in rows]).astype(np.int16),
+            "player": players}
+    df = pd.DataFrame(cols)
+    if with_features:
+        feats = np.stack([r["features"] for r in rows], axis=0) if n else np.zeros((0, 0), np.int16)
+        df = df.join(pd.DataFrame(feats, columns=["x_" + str(i) for i in range(feats.shape[1])], index=df.index))
+    pol = np.stack([r["pi"] for r in rows], axis=0) if n else np.zeros((0, 0))
+    df = df.join(pd.DataFrame(pol, columns=["pi_" + str(i) for i in range(pol.shape[1])], index=df.index))
+    df = df.join(pd.DataFrame(np.asarray([r["z"] for r in rows])[:, np.newaxis], columns=["z"], index=df.index))
+    stats = pd.DataFrame.from_records([r["stats"] for r in rows], columns=["max_deepness", "tree_size", "terminal_count", "q_value"],
+                                      index=df.index)
+    df = df.join(stats.astype({"max_deepness": np.int16, "tree_size": np.int32, "terminal_count": np.int32, "q_value": np.float32}))
+    df.set_index(["generation", "game_idx", "move_idx"], inplace=True)
+    return df
+
+
+class SelfPlay:
+    """self_play.py:19-156"""
+
+    def __init__(self, nn, params):
+        self.played_games = []
+        self.params = params
+        self.nn = nn
+        self.player_change_callback = lambda player: None
+
+    async def get_next_move(self, root_node, nb_mcts_searches, temperature, dirichlet):
+        mp = self.params.self_play.mcts
+        visit_counts = await mcts.UCT_search(root_node, nb_mcts_searches, self.nn, mp.mcts_cpuct, mp.max_async_searches, dirichlet)
+        probs = _apply_temperature(visit_counts, temperature)
+        return np.random.choice(probs.shape[0], 1, p=probs)[0]
+
+    async def play_game(self, game_state, idx):
+        temperature = None
+        seq = []
+        root = mcts.create_root_uct_node(game_state)
+        i = -1
+        while not root.is_terminal:
+            i += 1
+            self.player_change_callback(root.game_state.to_play)
+            params = self.params
+            if i in params.self_play.mcts.temperature:
+                temperature = params.self_play.mcts.temperature[i]
+            n_valid = len(root.game_state.get_valid_moves(as_indices=True))
+            move = await self.get_next_move(root, _n_searches(n_valid, params.self_play.mcts.mcts_num_read), temperature,
+                                            params.self_play.noise)
+            seq.append(root)
+            root = mcts.init_mcts_tree(root, move, reuse_tree=params.self_play.reuse_mcts_tree)
+        seq.append(root)
+        self.played_games.append((idx, seq, root.game_state.get_result()))
+
+    async def play_games(self, game_state, games_idxs, show_progress=False):
+        for idx in games_idxs:
+            if show_progress:
+                print(".", end="", flush=True)
+            await self.play_game(game_state, idx)
+
+    def get_games_moves(self):
+        moves, visit_counts = [], []
+        for _, seq, _ in self.played_games:
+            for node in seq[1:]:
+                moves.append(node.move)
+                visit_counts.append(node.child_number_visits)
+        return moves, np.asarray(visit_counts, dtype=float)
+
+    def set_player_change_callback(self, cb):
+        self.player_change_callback = cb
+
+    def get_datasets(self, generation, with_features=True):
+        rows = []
+        for game_idx, seq, z in self.played_games:
+            winner = seq[-1].game_state.just_played
+            for move_i, node in enumerate(seq[:-1]):
+                vis = node.child_number_visits
+                vs = vis.sum()
+                rows.append({"game_idx": game_idx, "move_idx": move_i, "move": node.move, "player": node.game_state.to_play,
+                             "z": z if node.game_state.to_play == winner else -z, "stats": tuple(node.get_tree_stats()),
+                             "pi": vis / (vs or 1.0),
+                             "features": node.game_state.get_features().ravel() if with_features else None})
+        return _dataset(rows, generation, with_features)
+
+
+class BatchedSelfPlay:
+    """`engine.n_games` self-play games in lock-step on one GPU.
+
+    evaluator(engine): fills engine.priors / engine.values from engine.planes (dotsboxesaz_b200.nn.DeviceEvaluator
+    or engine.FakeNetEvaluator).  seeds: one legacy-MT19937 seed per game; per move the stream yields the
+    Dirichlet draw (if alpha > 0) and then the uniform of np.random.choice, the reference's order.
+    """
+
+    def __init__(self, engine, evaluator, params, graph_waves=16):
+        self.eng = engine
+        self.ev = evaluator
+        self.params = params
+        self.graph_waves = graph_waves
+        self.played_games = []
+        self.rows = []
+        self.total_sims = 0
+
+    def play_games(self, games_idxs, seeds=None, start_states=None, with_features=True):
+        eng, sp = self.eng, self.params.self_play
+        n = eng.n_games
+        games_idxs = list(games_idxs)
+        assert len(games_idxs) <= n, "more games than engine slots"
+        active = np.zeros(n, dtype=bool)
+        active[:len(games_idxs)] = True
+        seeds = list(seeds) if seeds is not None else list(games_idxs)
+        rngs = [np.random.RandomState(s) for s in seeds] + [None] * (n - len(seeds))
+        alpha, coeff = sp.noise
+        num_read = sp.mcts.mcts_num_read
+        temp_sched = sp.mcts.temperature
+        eng.set_cpuct(sp.mcts.mcts_cpuct)
+        eng.reset_roots(start_states)
+        A = eng.A
+        temperature = [None] * n
+        hist = [[] for _ in range(n)]  # per game: row dicts of every searched root
+        moves_played = [[] for _ in range(n)]
+        move_i = -1
+        while active.any():
+            move_i += 1
+            roots = eng.root_states()
+            valid = eng.valid_moves(roots).cpu().numpy()
+            res = eng.result(roots).cpu().numpy()
+            feats = eng.features(roots, torch.int16).cpu().numpy().reshape(n, -1) if with_features else None
+            roots_np = eng.states_to_numpy(roots)
+            active &= (res == RESULT_NONE)
+            if not active.any():
+                break
+            reads = np.full(n, -1, dtype=np.int32)
+            noise = np.zeros((n, A), dtype=np.float64) if alpha > 0 else None
+            for g in np.flatnonzero(active):
+                if move_i in temp_sched:
+                    temperature[g] = temp_sched[move_i]
+                reads[g] = _n_searches(int(valid[g].sum()), num_read)
+                if alpha > 0:
+                    noise[g] = rngs[g].dirichlet(np.ones(A) * alpha, 1).ravel() * valid[g]
+            eng.run_search(torch.from_numpy(reads), self.ev, noise=None if noise is None else torch.from_numpy(noise),
+                           coeff=coeff, max_reads=int(reads.max()), graph_waves=self.graph_waves)
+            vis = eng.root_visits().cpu().numpy()
+            stats, _rW, q = (x.cpu().numpy() for x in eng.tree_stats())
+            moves = np.full(n, -1, dtype=np.int32)
+            for g in np.flatnonzero(active):
+                probs = _apply_temperature(vis[g], temperature[g])
+                r = rngs[g]
+                moves[g] = r.choice(A, 1, p=probs)[0]
+                hist[g].append({"game_idx": games_idxs[g], "move_idx": move_i, "move": moves_played[g][-1] if moves_played[g] else None,
+                                "player": int(roots_np["to_play"][g]), "visits": vis[g].copy(),
+                                "stats": (int(stats[g][1]), int(stats[g][2]), int(stats[g][3]), np.float32(q[g])),
+                                "features": feats[g].copy() if with_features else None})
+                moves_played[g].append(int(moves[g]))
+                self.total_sims += int(stats[g][0]) if False else 0
+            eng.advance_roots(moves, reuse=bool(sp.reuse_mcts_tree))
+        info = eng.status()
+        self.total_sims = info["sims"]
+        final = eng.states_to_numpy(eng.root_states())
+        res = eng.result(eng.root_states()).cpu().numpy()
+        for g in range(len(games_idxs)):
+            z = int(res[g])
+            winner = int(final["just_played"][g])
+            for r in hist[g]:
+                vs = r["visits"].sum()
+                r["pi"] = r["visits"] / (vs or 1.0)
+                r["z"] = z if r["player"] == winner else -z
+            self.rows.extend(hist[g])
+            self.played_games.append((games_idxs[g], moves_played[g], [r["visits"] for r in hist[g]], z))
+        return self.played_games
+
+    def get_games_moves(self):
+        moves, vcs = [], []
+        for _, mv, vis, _ in self.played_games:
+            moves.extend(mv)
+            vcs.extend(vis)
+        return moves, np.asarray(vcs, dtype=float)
+
+    def get_datasets(self, generation, with_features=True):
+        return _dataset(self.rows, generation, with_features)
+
+
+def shard_game_indices(n_games, rank, world):
+    """Games are independent: rank r plays the indices i with i % world == r (self_play.py:184 does the
+    same round-robin over devices with its worker pids)."""
+    return list(range(rank, n_games, world))
+
+
+def broadcast_model(model, src=0):
+    """The reference hands new weights to its self-play workers through model_gen{g}.pt on disk
+    (nn.py:272-273 -> self_play.py:188-190); here one flat NCCL/gloo broadcast of parameters + BN buffers."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    tensors = [p.data for p in model.parameters()] + [b.data for b in model.buffers()]
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dt, ts in by_dtype.items():
+        flat = torch.cat([t.reshape(-1) for t in ts])
+        dist.broadcast(flat, src=src)
+        off = 0
+        for t in ts:
+            t.copy_(flat[off:off + t.numel()].reshape(t.shape))
+            off += t.numel()
+
+
+def gather_samples(df, dst=0):
+    """Replaces the locked HDF append (self_play.py:264-265): every rank's sample rows end up on rank `dst`."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return df
+    out = [None] * dist.get_world_size() if dist.get_rank() == dst else None
+    dist.gather_object(df, out, dst=dst)
+    if dist.get_rank() != dst:
+        return None
+    return pd.concat(out).sort_index()
+
+
+def generate_games(hdf_file_name, generation, nn_class, n_games, params, n_workers=None, games_per_workers=10,
+                   engine=None, evaluator=None, writer=None):
+    """self_play.py:291-306.  One process per GPU (torch.distributed), `n_games` sharded by index; each rank
+    plays its shard in lock-step batches of engine.n_games.  Rank 0 receives all sample rows and hands them
+    to `writer(hdf_file_name, "fresh", df)` (default: pandas HDFStore append, as utils/utils.py:94-96)."""
+    import torch.distributed as dist
+    from . import engine as _engine
+    from .nn import DeviceEvaluator
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    mine = shard_game_indices(n_games, rank, world)
+    if engine is None:
+        slots = max(1, min(len(mine), int(params.self_play.get("concurrent_games", 4096) or 4096)))
+        engine = _engine.Engine(tuple(params.game.clazz.BOARD_DIM), n_games=slots,
+                                max_nodes=int(params.self_play.get("max_nodes_per_tree", 8192) or 8192))
+    if evaluator is None:
+        model = nn_class(params)
+        if generation != 0:
+            model.load_parameters(generation - 1, to_device=engine.device)
+        broadcast_model(model.to(engine.device))
+        evaluator = DeviceEvaluator(model, engine)
+    frames = []
+    for lo in range(0, len(mine), engine.n_games):
+        chunk = mine[lo:lo + engine.n_games]
+        sp = BatchedSelfPlay(engine, evaluator, params)
+        sp.play_games(chunk, seeds=[int(params.self_play.get("seed", 0) or 0) + i for i in chunk])
+        frames.append(sp.get_datasets(generation, True))
+    df = pd.concat(frames) if frames else None
+    df = gather_samples(df)
+    if rank == 0 and df is not None:
+        df["training"] = np.zeros(len(df.index), dtype=np.int8)
+        if writer is None:
+            from .utils.utils import write_to_hdf as writer
+        writer(hdf_file_name, "fresh", df)
+    return df

@@ -104,7 +104,8 @@ int dbaz_game_random_rollout(dbaz_engine *e, dbaz_state *states, uint64_t seed, 
 /* ---- search: one tree per game, strictly sequential simulations per tree ---- */
 /* create_root_uct_node (mcts.py:156-160) for all n_games trees */
 int dbaz_search_reset_roots(dbaz_engine *e, const dbaz_state *root_states, uint64_t stream);
-/* Head of UCT_search (mcts.py:205-229).  num_reads int32[n_games] (0 = tree idle this search).
+/* Head of UCT_search (mcts.py:205-229).  num_reads int32[n_games] (-1 = tree idle this search;
+ * -2 = only the initial _search() of an unexpanded root, without the prior mix).
  * noise float64[n_games][A] = Dirichlet sample already multiplied by the legal mask
  * (mcts.py:220-223) or NULL when alpha <= 0; coeff = dirichlet[1].  Unexpanded roots get the extra
  * initial _search() (mcts.py:207-208) before the prior mix, exactly as the reference orders it.
@@ -119,6 +120,9 @@ int dbaz_search_begin(dbaz_engine *e, const int32_t *num_reads, const double *no
  *   2 = terminal (net output ignored). */
 int dbaz_search_step(dbaz_engine *e, const float *priors, const float *values, void *planes, int32_t dtype,
                      int32_t layout, dbaz_state *leaf_states, int8_t *leaf_kind, uint64_t stream);
+/* UCT_search's wall-clock limit (mcts.py:201-203,232-233): no tree starts another simulation; the
+ * next dbaz_search_step() only backs up the leaves already pending. */
+int dbaz_search_stop(dbaz_engine *e, uint64_t stream);
 /* root.child_number_visits (mcts.py:244): int32[n_games][A] */
 int dbaz_search_root_visits(dbaz_engine *e, int32_t *out, uint64_t stream);
 /* Root node view: any of W float32[n][A], priors float64[n][A], sign int32[n][A], ucb float64[n][A]

@@ -1,0 +1,163 @@
+"""GPU: the reference-facing Python surface (BoxesState / mcts / SelfPlay / BatchedSelfPlay) against
+fixtures recorded from the real reference.  The tests read like the reference's own usage."""
+import asyncio
+import warnings
+
+import numpy as np
+import pytest
+
+from golden_io import load, unhex
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+GAMES = load("games")
+MCTS = load("mcts")
+SELFPLAY = load("selfplay")
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dotsboxesaz_b200 import mcts, self_play, engine
+    from dotsboxesaz_b200.dots_boxes.dots_boxes_game import BoxesState, nn_batch_builder
+    from dotsboxesaz_b200.utils.utils import DotDict
+    return dict(mcts=mcts, self_play=self_play, engine=engine, BoxesState=BoxesState, nn_batch_builder=nn_batch_builder,
+                DotDict=DotDict)
+
+
+def fake_nn_eval(state, kind):
+    A = state.get_actions_size()
+    h = int(state.get_hash()[0]) & 0xFFFFFFFF
+    if kind == 0:
+        raw = np.array([float((h * 2654435761 + i * 40503) % 1024) + 1 for i in range(A)], dtype=np.float32)
+        return raw / raw.sum(), np.array([((h % 2001) - 1000) / 1000], dtype=np.float32)
+    return (np.full(A, np.float32(1.0) / np.float32(A), dtype=np.float32),
+            np.array([(((h * 31) % 5) - 2) / 2], dtype=np.float32))
+
+
+def make_nn(kind):
+    async def nn(state):
+        return fake_nn_eval(state, kind)
+    return nn
+
+
+def test_boxes_state_surface(api):
+    BoxesState = api["BoxesState"]
+    for G in [GAMES[0], GAMES[25], GAMES[34], GAMES[40]]:
+        BoxesState.init_static_fields(((G["L"], G["C"]),))
+        assert BoxesState.NB_ACTIONS == 2 * (G["L"] + 1) * (G["C"] + 1) and BoxesState.NB_BOXES == G["L"] * G["C"]
+        s = BoxesState()
+        assert s.hash == (0, 0) and s.just_played is None and s.to_play == 0 and s.get_result() is None
+        assert bytes(s.board.ravel().tolist()).hex() == G["init"]["board"]
+        states = [s]
+        for P in G["plies"]:
+            t = s.play(P["move"])                      # play() clones
+            assert s.hash != t.hash or P["move"] is None
+            closed = s.play_(P["move"])                # play_() mutates
+            assert s == t and hash(s) == hash(t)
+            assert [list(x) for x in closed] == P["closed"]
+            assert bytes(s.board.ravel().tolist()).hex() == P["board"]
+            assert s.to_play == P["to_play"] and (-1 if s.just_played is None else s.just_played) == P["just_played"]
+            assert [int(round(2 * x)) for x in s.boxes_to_close] == P["btc2"]
+            assert (2 if s.get_result() is None else s.get_result()) == P["result"]
+            assert str(s.get_hash()[0]) == P["hash0"] and int(round(2 * s.get_hash()[1])) == P["hash1_x2"]
+            assert np.array_equal(s.get_valid_moves(), unhex(P["valid"], np.uint8).astype(bool))
+            assert s.get_valid_moves(as_indices=True) == np.flatnonzero(unhex(P["valid"], np.uint8)).tolist()
+            f = s.get_features()
+            assert f.dtype == np.int16 and f.shape == BoxesState.FEATURES_SHAPE
+            assert np.array_equal(f.ravel().astype(np.int8), unhex(P["features"], np.int8))
+            states.append(t)
+        for a, _ in G["illegal"]:
+            with pytest.raises(ValueError):
+                s.play(a)
+        batch = api["nn_batch_builder"](*[(x,) for x in states[1:4]])
+        assert batch.shape == (len(states[1:4]), 3, G["L"] + 1, G["C"] + 1)
+        assert np.array_equal(batch[0].ravel().astype(np.int8), unhex(G["plies"][0]["features"], np.int8))
+        assert "To play" in repr(s)
+    BoxesState.init_static_fields(((3, 3),))
+
+
+@pytest.mark.parametrize("si", [0, 3, 10, 11, 12, 13, 14, 20, 33])
+def test_uct_search_dropin(api, si):
+    """create_root_uct_node / UCT_search(max_pending_evals=1) / init_mcts_tree with a Python async nn."""
+    warnings.filterwarnings("ignore")
+    m, BoxesState = api["mcts"], api["BoxesState"]
+    S = MCTS[si]
+    BoxesState.init_static_fields(((S["L"], S["C"]),))
+    s = BoxesState()
+    for mv in S["pre_moves"]:
+        s.play_(mv)
+    root = m.create_root_uct_node(s)
+    if S["seed"] is not None:
+        np.random.seed(S["seed"])
+    nn = make_nn(S["kind"])
+    steps = S["steps"][:12]
+    for i, st in enumerate(steps):
+        if st["op"] == "search":
+            vis = asyncio.run(m.UCT_search(root, st["num_reads"], nn, cpuct=tuple(S["cpuct"]), max_pending_evals=1,
+                                           dirichlet=(st["alpha"], st["coeff"])))
+            assert vis.dtype == np.int32 and vis.tolist() == st["root"]["visits"], (si, i)
+        else:
+            prev = root
+            root = m.init_mcts_tree(root, st["move"], reuse_tree=st["reuse"])
+            assert prev.child_number_visits.tolist() == steps[i - 1]["root"]["visits"]  # frozen for sample extraction
+        ref = st["root"]
+        assert np.array_equal(root.child_total_value, unhex(ref["W"], np.float32))
+        assert np.array_equal(root.child_priors, unhex(ref["priors"], np.float64))
+        assert np.array_equal(root.children_ucb_score(), unhex(ref["ucb"], np.float64))
+        assert root.number_visits == ref["root_N"] and np.float32(root.total_value) == np.float32(ref["root_W"])
+        assert root.is_terminal == ref["is_terminal"] and root.is_expanded == ref["is_expanded"]
+        ts = root.get_tree_stats()
+        assert [int(ts.max_deepness), int(ts.tree_size), int(ts.terminal_count)] == ref["stats"][:3]
+        assert np.float32(ts.q_value) == np.float32(ref["stats"][3])
+        assert root.parent.get_tree_stats() == ts
+    BoxesState.init_static_fields(((3, 3),))
+
+
+def _params(api, G):
+    return api["DotDict"]({"self_play": {"reuse_mcts_tree": True, "noise": tuple(G["noise"]),
+                                         "mcts": {"mcts_num_read": G["num_read"], "mcts_cpuct": (1.25, 19652),
+                                                  "temperature": {int(k): v for k, v in G["temperature"].items()},
+                                                  "max_async_searches": 1}}})
+
+
+@pytest.mark.parametrize("gi", [0, 4, 6])
+def test_selfplay_dropin(api, gi):
+    """SelfPlay.play_game + get_datasets, seeded like the reference run that produced the fixture."""
+    warnings.filterwarnings("ignore")
+    G = SELFPLAY[gi]
+    BoxesState = api["BoxesState"]
+    BoxesState.init_static_fields(((G["L"], G["C"]),))
+    sp = api["self_play"].SelfPlay(make_nn(G["kind"]), _params(api, G))
+    np.random.seed(G["seed"])
+    asyncio.run(sp.play_game(BoxesState(), G["seed"]))
+    idx, seq, z = sp.played_games[0]
+    assert [int(n.move) for n in seq[1:]] == G["moves"]
+    assert [n.child_number_visits.tolist() for n in seq[:-1]] == G["visits"]
+    assert z == G["z"]
+    df = sp.get_datasets(3, with_features=True).reset_index()
+    assert list(df.columns) == G["columns"]
+    got = df.to_numpy(dtype=np.float64)
+    ref = np.array(G["rows"], dtype=np.float64)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    BoxesState.init_static_fields(((3, 3),))
+
+
+def test_batched_selfplay_matches_reference_games(api):
+    """All recorded 3x3 / 100-sim reference games at once, in lock-step on one engine, each with its own
+    legacy RNG stream: same moves, visit counts and dataset rows as the reference played sequentially."""
+    games = [G for G in SELFPLAY if (G["L"], G["C"], G["num_read"], G["kind"]) == (3, 3, 100, 0)]
+    assert len(games) >= 3
+    eng = api["engine"].Engine((3, 3), n_games=len(games) + 1, max_nodes=2048)  # one idle slot on purpose
+    for graph_waves in (0, 8):
+        bsp = api["self_play"].BatchedSelfPlay(eng, api["engine"].FakeNetEvaluator(0), _params(api, games[0]), graph_waves=graph_waves)
+        played = bsp.play_games([G["seed"] for G in games], seeds=[G["seed"] for G in games])
+        for (idx, moves, visits, z), G in zip(played, games):
+            assert moves == G["moves"] and [v.tolist() for v in visits] == G["visits"] and z == G["z"]
+        df = bsp.get_datasets(3, True).reset_index()
+        ref_rows = np.concatenate([np.array(G["rows"], dtype=np.float64) for G in games])
+        assert list(df.columns) == games[0]["columns"]
+        assert np.array_equal(df.to_numpy(dtype=np.float64), ref_rows)
+    eng.close()
