@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--sims", type=int, default=800, help="simulations per move")
     ap.add_argument("--net", default="simple", choices=["simple", "resnet", "fake"])
     ap.add_argument("--net-dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--net-plan", default="fused", choices=["fused", "module"],
+                    help="fused: library convs/GEMMs + the engine's fused epilogue kernels; module: the plain nn.Module")
     ap.add_argument("--graph-waves", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="processes for the CPU baseline (0 = min(cores-1, 64))")
@@ -208,7 +210,7 @@ def main():
     import torch
     import torch.distributed as dist
     from dotsboxesaz_b200 import engine
-    from dotsboxesaz_b200.nn import DeviceEvaluator, ResNetZero, resnet_zero_parameters
+    from dotsboxesaz_b200.nn import (DeviceEvaluator, FusedResNetZero, FusedSimpleNN, ResNetZero, resnet_zero_parameters)
     from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
     from dotsboxesaz_b200.utils.utils import DotDict
 
@@ -226,7 +228,10 @@ def main():
         torch.manual_seed(0)
         model = SimpleNN(board=(L, C)) if args.net == "simple" else ResNetZero(
             DotDict({"nn": {"model_parameters": resnet_zero_parameters((L, C))}}))
-        ev = DeviceEvaluator(model, eng, dtype=dt, channels_last=True)
+        if args.net_plan == "fused":
+            ev = (FusedSimpleNN if args.net == "simple" else FusedResNetZero)(model, eng, dtype=dt)
+        else:
+            ev = DeviceEvaluator(model, eng, dtype=dt, channels_last=True)
 
     roots = synthetic_roots(eng, torch, seed=1234 + rank)
     valid_np = eng.valid_moves(roots).cpu().numpy()
@@ -336,7 +341,7 @@ def main():
                 "dtype": "f64 PUCT over f32/i32 node stats; net %s" % (args.net_dtype if args.net != "fake" else "none (fake)"),
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "board": args.board, "games_per_gpu": args.games,
-                           "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "parallelism": "games sharded by index x%d, no collective" % world,
+                           "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "net_plan": args.net_plan, "parallelism": "games sharded by index x%d, no collective" % world,
                            "l2": "inputs larger than L2: node pool touched per step %.2f GB/GPU vs 126 MB L2" % (
                                args.games * (args.sims + 1) * eng.node_bytes / 1e9),
                            "graph_waves": args.graph_waves},

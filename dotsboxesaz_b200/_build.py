@@ -7,7 +7,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libdbaz_b200.so")
 SOURCES = ["dbaz_capi.cu"]
-HEADERS = ["dbaz_device.cuh", "dbaz_game_kernels.cuh", "dbaz_tree_kernels.cuh"]
+HEADERS = ["dbaz_device.cuh", "dbaz_game_kernels.cuh", "dbaz_tree_kernels.cuh", "dbaz_nn_kernels.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-I" + INCLUDE]
 

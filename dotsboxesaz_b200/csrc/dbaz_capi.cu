@@ -1,6 +1,8 @@
 // dbaz_capi.cu -- the extern "C" boundary declared in include/dbaz_b200.h.
 // Plain pointers and sizes only; no torch types.  Built in-tree for sm_100a:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC ...
+#include <algorithm>
+#include <numeric>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -8,6 +10,7 @@
 #include <vector>
 
 #include "dbaz_game_kernels.cuh"
+#include "dbaz_nn_kernels.cuh"
 #include "dbaz_tree_kernels.cuh"
 
 using namespace dbaz;
@@ -144,6 +147,8 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
               alloc((void**)&ta.root_prior, (size_t)ta.n_trees * A * sizeof(double), "root priors") &&
               alloc((void**)&ta.path, (size_t)ta.n_trees * PATH_CAP * sizeof(uint32_t), "paths") &&
               alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double), "log table") &&
+              alloc((void**)&ta.act_tab, (size_t)A * 2 * sizeof(uint4), "action table") &&
+              alloc((void**)&ta.leaf_hdr, (size_t)ta.n_trees * 2 * sizeof(uint4), "leaf headers") &&
               alloc((void**)&e->d_status, 8 * sizeof(unsigned long long), "status");
     if (!ok) { dbaz_engine_destroy(e); return 1; }
     if (upload_lut(e)) { g_create_err = e->err; dbaz_engine_destroy(e); return 1; }
@@ -155,6 +160,9 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
         cudaError_t s2 = cudaFuncSetAttribute(k_advance_roots<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
         if (s1 != cudaSuccess || s2 != cudaSuccess) { g_create_err = "cannot reserve shared memory for re-rooting"; dbaz_engine_destroy(e); return 1; }
     }
+    k_build_act_tab<<<1, DBAZ_MAX_ACTIONS>>>(b, const_cast<uint4*>(ta.act_tab));
+    cudaMemset(ta.leaf_hdr, 0, (size_t)ta.n_trees * 2 * sizeof(uint4));
+    cudaMemset(ta.path, 0, (size_t)ta.n_trees * PATH_CAP * sizeof(uint32_t));
     // an all-empty-board root set so that the engine is usable right after create
     k_reset_roots<<<blocks_for(ta.n_trees, 128), 128>>>(b, ta, nullptr);
     if ((st = cudaDeviceSynchronize()) != cudaSuccess) { cuda_fail(nullptr, "k_reset_roots", st); dbaz_engine_destroy(e); return 1; }
@@ -170,6 +178,8 @@ void dbaz_engine_destroy(dbaz_engine* e) {
     cudaFree(e->ta.root_prior);
     cudaFree(e->ta.path);
     cudaFree(const_cast<double*>(e->ta.lut));
+    cudaFree(const_cast<uint4*>(e->ta.act_tab));
+    cudaFree(e->ta.leaf_hdr);
     cudaFree(e->d_status);
     delete e;
 }
@@ -256,6 +266,61 @@ int dbaz_fake_nn(dbaz_engine* e, const dbaz_state* leaf_states, float* priors, f
     DeviceGuard guard(e->cfg.device);
     k_fake_nn<<<blocks_for(n * 32, 256), 256, 0, S(stream)>>>(e->board, leaf_states, priors, values, kind, n);
     return launch_ok(e, "k_fake_nn");
+}
+
+/* ------------------------------------------------- leaf-eval fused stages */
+
+int dbaz_nn_epilogue(dbaz_engine* e, void* x, const void* res, const float* bias, const float* scale, const float* shift,
+                     int64_t rows, int32_t channels, int32_t dtype, int32_t mode, uint64_t stream) {
+    if (!e || !x || !scale || !shift) return 1;
+    if (mode < 0 || mode > 2) return fail(e, "bad epilogue mode");
+    if (rows <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    const int per = dtype == DBAZ_F32 ? 4 : 8;
+    if (dtype != DBAZ_F32 && dtype != DBAZ_BF16 && dtype != DBAZ_F16) return fail(e, "bad dtype");
+    if (channels % per) return fail(e, "channels must be a multiple of the vector width");
+    const int cv = channels / per;
+    const int64_t n_vec64 = rows * cv;
+    if (n_vec64 >= (int64_t)1 << 31) return fail(e, "epilogue tensor too large");
+    const uint32_t n_vec = (uint32_t)n_vec64;
+    // total threads must be a multiple of cv so that each thread owns a fixed channel group
+    int block = 256;
+    while (block % cv && block > 32) block >>= 1;
+    int64_t want = std::min<int64_t>((n_vec + (int64_t)block * 4 - 1) / ((int64_t)block * 4), (int64_t)e->n_sms * 8);
+    int grid = (int)std::max<int64_t>(want, 1);
+    if ((int64_t)block % cv) {  // cv does not divide the block: make the grid supply the multiple
+        int g = cv / std::__gcd(cv, block);
+        grid = (grid + g - 1) / g * g;
+    }
+#define DBAZ_EPI(KERNEL, TYPE)                                                                                     \
+    do {                                                                                                           \
+        if (mode == 0) KERNEL<TYPE, 0><<<grid, block, 0, S(stream)>>>((TYPE*)x, (const TYPE*)res, bias, scale, shift, n_vec, channels); \
+        else if (mode == 1) KERNEL<TYPE, 1><<<grid, block, 0, S(stream)>>>((TYPE*)x, (const TYPE*)res, bias, scale, shift, n_vec, channels); \
+        else KERNEL<TYPE, 2><<<grid, block, 0, S(stream)>>>((TYPE*)x, (const TYPE*)res, bias, scale, shift, n_vec, channels); \
+    } while (0)
+    if (dtype == DBAZ_BF16) DBAZ_EPI(k_nn_epilogue16, __nv_bfloat16);
+    else if (dtype == DBAZ_F16) DBAZ_EPI(k_nn_epilogue16, __half);
+    else {
+        if (mode == 0) k_nn_epilogue32<0><<<grid, block, 0, S(stream)>>>((float*)x, (const float*)res, bias, scale, shift, n_vec, channels);
+        else if (mode == 1) k_nn_epilogue32<1><<<grid, block, 0, S(stream)>>>((float*)x, (const float*)res, bias, scale, shift, n_vec, channels);
+        else k_nn_epilogue32<2><<<grid, block, 0, S(stream)>>>((float*)x, (const float*)res, bias, scale, shift, n_vec, channels);
+    }
+#undef DBAZ_EPI
+    return launch_ok(e, "k_nn_epilogue");
+}
+
+int dbaz_nn_heads(dbaz_engine* e, const void* logits, int32_t ld, int32_t dtype, float* priors, float* values, int64_t n,
+                  uint64_t stream) {
+    if (!e || !logits || !priors || !values) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    const int A = e->board.A;
+    const int grid = blocks_for(n * 32, 256);
+    if (dtype == DBAZ_BF16) k_nn_heads<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)logits, ld, A, priors, values, n);
+    else if (dtype == DBAZ_F16) k_nn_heads<__half><<<grid, 256, 0, S(stream)>>>((const __half*)logits, ld, A, priors, values, n);
+    else if (dtype == DBAZ_F32) k_nn_heads<float><<<grid, 256, 0, S(stream)>>>((const float*)logits, ld, A, priors, values, n);
+    else return fail(e, "bad dtype");
+    return launch_ok(e, "k_nn_heads");
 }
 
 /* ---------------------------------------------------------------- search */

@@ -198,10 +198,8 @@ __device__ __forceinline__ float feature_value(const Board& b, const Mask<NW>& e
 // Warp-cooperative: writes the F elements of one row.  When F % 4 == 0 every lane stores 4
 // consecutive elements with one 16-byte (fp32) or 8-byte (16-bit types) vector store.
 template <int NW>
-__device__ __forceinline__ void write_planes_warp(const Board& b, const dbaz_state& s, void* planes, int64_t row,
+__device__ __forceinline__ void write_planes_warp(const Board& b, const Mask<NW>& e, int k, void* planes, int64_t row,
                                                   int dtype, int layout, int lane) {
-    Mask<NW> e = load_edges<NW>(s);
-    int k = (int)(int8_t)s.btc2[s.to_play];
     const int F = b.F;
     if ((F & 3) == 0) {
         for (int q = lane; q < (F >> 2); q += 32) {

@@ -67,7 +67,7 @@ __global__ void k_game_features(Board b, const dbaz_state* __restrict__ states, 
     int lane = threadIdx.x & 31;
     if (w >= n) return;
     dbaz_state s = states[w];
-    write_planes_warp<NW>(b, s, planes, w, dtype, layout, lane);
+    write_planes_warp<NW>(b, load_edges<NW>(s), (int)(int8_t)s.btc2[s.to_play], planes, w, dtype, layout, lane);
 }
 
 // Uniform random legal playout to terminal; the whole game runs in registers, HBM sees the

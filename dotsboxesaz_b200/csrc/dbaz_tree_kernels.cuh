@@ -57,6 +57,8 @@ struct TreeArgs {
     double* root_prior;   // [n_trees][A]
     uint32_t* path;       // [n_trees][PATH_CAP]
     const double* lut;    // c0(N) = log((N + base + 1)/base) + cpuct, host libm
+    const uint4* act_tab; // [A][2]: the two box masks each action borders (built once per engine)
+    uint4* leaf_hdr;      // [n_trees][2]: copy of the pending leaf's header (saves a dependent load per wave)
     int lut_size;
     int n_trees;
     int max_nodes;
@@ -82,6 +84,57 @@ __device__ __forceinline__ void store_hdr(char* np, const dbaz_state& s) {
 }
 __device__ __forceinline__ Child* node_children(char* np) { return reinterpret_cast<Child*>(np + 32); }
 
+// The 32-byte node header unpacked into registers (same byte layout as dbaz_state; going through the
+// struct would spill it to local memory).
+struct Hdr {
+    uint64_t e0, e1;
+    int btc0, btc1, to_play, just_played, flags, depth, parent, parent_action, result;
+};
+__device__ __forceinline__ Hdr unpack_hdr(const uint4& a, const uint4& b) {
+    Hdr h;
+    h.e0 = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    h.e1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    h.btc0 = (int)(int16_t)(b.x & 0xffffu); h.btc1 = (int)(int16_t)(b.x >> 16);
+    h.to_play = b.y & 0xffu; h.just_played = (int)(int8_t)((b.y >> 8) & 0xffu);
+    h.flags = (b.y >> 16) & 0xffu; h.depth = (b.y >> 24) & 0xffu;
+    h.parent = (int)b.z;
+    h.parent_action = (int)(int16_t)(b.w & 0xffffu); h.result = (int)(int16_t)(b.w >> 16);
+    return h;
+}
+__device__ __forceinline__ void pack_hdr(const Hdr& h, uint4& a, uint4& b) {
+    a.x = (uint32_t)h.e0; a.y = (uint32_t)(h.e0 >> 32); a.z = (uint32_t)h.e1; a.w = (uint32_t)(h.e1 >> 32);
+    b.x = ((uint32_t)h.btc0 & 0xffffu) | ((uint32_t)h.btc1 << 16);
+    b.y = ((uint32_t)h.to_play & 0xffu) | (((uint32_t)h.just_played & 0xffu) << 8) | (((uint32_t)h.flags & 0xffu) << 16) |
+          (((uint32_t)h.depth & 0xffu) << 24);
+    b.z = (uint32_t)h.parent;
+    b.w = ((uint32_t)h.parent_action & 0xffffu) | ((uint32_t)h.result << 16);
+}
+__device__ __forceinline__ Hdr load_hdr_regs(const char* np) {
+    const uint4* p = reinterpret_cast<const uint4*>(np);
+    uint4 a = p[0], b = p[1];
+    return unpack_hdr(a, b);
+}
+__device__ __forceinline__ void store_hdr_regs(char* np, const Hdr& h) {
+    uint4 a, b;
+    pack_hdr(h, a, b);
+    uint4* p = reinterpret_cast<uint4*>(np);
+    p[0] = a; p[1] = b;
+}
+__device__ __forceinline__ int hdr_result(const Hdr& h) {  // dots_boxes_game.py:51-59
+    const int mine = h.to_play ? h.btc1 : h.btc0, other = h.to_play ? h.btc0 : h.btc1;
+    if (h.btc0 == 0 && h.btc1 == 0) return 0;
+    if (mine < 0) return 1;
+    if (other < 0) return -1;
+    return DBAZ_RESULT_NONE;
+}
+template <int NW>
+__device__ __forceinline__ Mask<NW> hdr_edges(const Hdr& h) {
+    Mask<NW> m;
+    m.w[0] = h.e0;
+    if (NW == 2) m.w[NW - 1] = h.e1;
+    return m;
+}
+
 __device__ __forceinline__ double puct_c0(const TreeArgs& ta, int N) {
     if (N < ta.lut_size) return ta.lut[N];
     // beyond the host table: device log (<= 1 ulp from libm; documented in DESIGN.md)
@@ -94,18 +147,18 @@ template <int APL, int NW>
 struct LaneActions {
     Mask<NW> box[APL][2];
     bool real[APL];
-    __device__ __forceinline__ void init(const Board& b, int lane) {
+    __device__ __forceinline__ void load(const Board& b, const uint4* __restrict__ tab, int lane) {
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
-            int a = lane + 32 * k;
-            int lc[2][2];
+            const int a = lane + 32 * k;
             real[k] = a < b.A && ((b.real[a >> 6] >> (a & 63)) & 1ull);
-            if (a < b.A) action_boxes<NW>(b, a, box[k], lc);
-            else {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int i = 0; i < NW; ++i) box[k][j].w[i] = 0;
+            uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+            if (a < b.A) { m0 = tab[2 * a]; m1 = tab[2 * a + 1]; }
+            box[k][0].w[0] = (uint64_t)m0.x | ((uint64_t)m0.y << 32);
+            box[k][1].w[0] = (uint64_t)m1.x | ((uint64_t)m1.y << 32);
+            if (NW == 2) {
+                box[k][0].w[NW - 1] = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
+                box[k][1].w[NW - 1] = (uint64_t)m1.z | ((uint64_t)m1.w << 32);
             }
         }
     }
@@ -116,6 +169,17 @@ struct LaneActions {
         return closed_count<NW>(ea, box[k]);
     }
 };
+
+// one thread per action: the two box masks the action borders, in play_'s test order
+__global__ void k_build_act_tab(Board b, uint4* __restrict__ tab) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= b.A) return;
+    Mask<2> box[2];
+    int lc[2][2];
+    action_boxes<2>(b, a, box, lc);
+    for (int j = 0; j < 2; ++j)
+        tab[2 * a + j] = make_uint4((uint32_t)box[j].w[0], (uint32_t)(box[j].w[0] >> 32), (uint32_t)box[j].w[1], (uint32_t)(box[j].w[1] >> 32));
+}
 
 // One PUCT level (mcts.py:91-103), float64 with every operation individually rounded (no FMA):
 //   pb_c = c0(N) * (sqrt(N) / (n_i + 1)); score_i = pb_c * prior_i + (W_i / (1 + n_i)) * sign_i
@@ -197,14 +261,23 @@ __device__ __forceinline__ void root_prior_mix(const Board& b, const TreeArgs& t
     __syncwarp();
 }
 
+// Values every lane preloads at kernel entry with loads that do not depend on each other: the
+// tree record, the pending leaf's header copy, its path and its net outputs (one round trip).
+template <int APL>
+struct StepInputs {
+    uint4 lh0, lh1;     // pending leaf header
+    uint32_t pe[PATH_CAP / 32];
+    float p[APL];
+    float value;
+};
+
 // expand + backup of the pending leaf (mcts.py:116-132 and the prior masking of 188-196)
 template <int APL, int NW>
 __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArgs& ta, int t, TreeRec& T,
-                                                   const float* __restrict__ priors, const float* __restrict__ values,
-                                                   double* sh, int lane) {
+                                                   const StepInputs<APL>& in, double* sh, int lane) {
     const int A = b.A;
     char* lp = node_ptr(ta, t, T.leaf);
-    dbaz_state lh = load_hdr(lp);
+    Hdr lh = unpack_hdr(in.lh0, in.lh1);
     const bool terminal = lh.flags & NF_TERMINAL;
     float value;
     if (!terminal) {
@@ -215,9 +288,9 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
         for (int k = 0; k < APL; ++k) {
             int a = lane + 32 * k;
             if (a < A) {
-                float x = priors[(int64_t)t * A + a];
-                bool legal = ((b.real[NW == 1 ? 0 : (a >> 6)] & ~lh.edges[NW == 1 ? 0 : (a >> 6)]) >> (a & 63)) & 1ull;
-                p[k] = legal ? x : __fmul_rn(x, 0.0f);
+                const uint64_t ed = (NW == 1 || a < 64) ? lh.e0 : lh.e1;
+                bool legal = ((b.real[NW == 1 ? 0 : (a >> 6)] & ~ed) >> (a & 63)) & 1ull;
+                p[k] = legal ? in.p[k] : __fmul_rn(in.p[k], 0.0f);
                 shf[a] = p[k];
             }
         }
@@ -225,16 +298,16 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
         float s = np_sum<float>(shf, A);
         __syncwarp();
         Child* ch = node_children(lp);
+        const bool renorm = (s > 0.0f && s != 1.0f);
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
             int a = lane + 32 * k;
             if (a < A) {
-                float q = (s > 0.0f && s != 1.0f) ? __fdiv_rn(p[k], s) : p[k];
-                Child c; c.W = 0.0f; c.N = 0; c.prior = q; c.child = 0;
-                *reinterpret_cast<int4*>(&ch[a]) = *reinterpret_cast<int4*>(&c);
+                float q = renorm ? __fdiv_rn(p[k], s) : p[k];
+                *reinterpret_cast<uint4*>(&ch[a]) = make_uint4(0u, 0u, __float_as_uint(q), 0u);  // {W=0, N=0, prior, child=none}
             }
         }
-        value = values[t];
+        value = in.value;
     } else {
         value = (float)lh.result;  // get_result(): python int 1 / 0
         if (T.leaf == 0) {
@@ -247,25 +320,29 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
     }
     if (!(lh.flags & NF_EXPANDED) && lane == 0) {
         lh.flags |= NF_EXPANDED;
-        reinterpret_cast<int4*>(lp)[1] = reinterpret_cast<int4*>(&lh)[1];
+        uint4 a4, b4;
+        pack_hdr(lh, a4, b4);
+        reinterpret_cast<uint4*>(lp)[1] = b4;
     }
     // backup: every path node gets W += v*s + 1 and N += 1; all but the leaf also carry the
     // virtual loss subtracted on the way down (W - 1 first, as its own float32 rounding step).
-    const uint32_t* path = ta.path + (int64_t)t * PATH_CAP;
     const int plen = T.path_len;
-    for (int j = lane; j < plen; j += 32) {
-        uint32_t pe = path[j];
-        int tp = pe >> 31;
-        float v = (tp == (int)lh.to_play) ? value : -value;
-        float add = __fadd_rn(v, 1.0f);
-        bool is_leaf = (j == plen - 1);
+#pragma unroll
+    for (int i = 0; i < PATH_CAP / 32; ++i) {
+        const int j = lane + 32 * i;
+        if (j >= plen) continue;
+        const uint32_t pe = in.pe[i];
+        const int tp = pe >> 31;
+        const float v = (tp == lh.to_play) ? value : -value;
+        const float add = __fadd_rn(v, 1.0f);
+        const bool is_leaf = (j == plen - 1);
         if (j == 0) {
             float W = T.root_W;
             if (!is_leaf) W = __fsub_rn(W, 1.0f);
             T.root_W = __fadd_rn(W, add);  // only lane 0 reaches j == 0; T is written back by lane 0
             T.root_N += 1;
         } else {
-            int parent = (pe & 0x7fffffffu) >> 8, act = pe & 0xffu;
+            const int parent = (pe & 0x7fffffffu) >> 8, act = pe & 0xffu;
             float2* cell = reinterpret_cast<float2*>(&node_children(node_ptr(ta, t, parent))[act]);
             float2 wn = *cell;
             float W = wn.x;
@@ -277,19 +354,35 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
     }
     if (lane == 0) {
         T.terminal_count += terminal ? 1 : 0;
-        T.max_deepness = max(T.max_deepness, (int)lh.depth);
+        T.max_deepness = max(T.max_deepness, lh.depth);
         T.total_term += terminal ? 1 : 0;
-        T.leaf = -1;
         T.total_sims += 1;
         T.total_path += plen;
     }
+    T.leaf = -1;
+}
+
+// Warp argmax of (score, lowest action id wins ties) with three REDUX operations on an
+// order-preserving integer image of the float64 score instead of 15 shuffles.
+__device__ __forceinline__ int warp_argmax(double best, int best_a) {
+    unsigned long long key = 0ull;
+    if (best_a != 0x7fffffff) {
+        unsigned long long u = (unsigned long long)__double_as_longlong(__dadd_rn(best, 0.0));  // -0.0 -> +0.0
+        key = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    }
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const bool c1 = (hi == mh) && best_a != 0x7fffffff;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, c1 ? lo : 0u);
+    const bool c2 = c1 && lo == ml;
+    return (int)__reduce_min_sync(0xffffffffu, c2 ? (unsigned)best_a : 0x7fffffffu);
 }
 
 // select_leaf with lazy child creation (mcts.py:105-114).  Returns the leaf kind
 // (1 = needs evaluation, 2 = terminal) and leaves the leaf header in `leaf_hdr`.
 template <int APL, int NW>
 __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, int t, TreeRec& T,
-                                           const LaneActions<APL, NW>& la, dbaz_state& leaf_hdr, int lane) {
+                                           const LaneActions<APL, NW>& la, Hdr& leaf_hdr, int lane) {
     const int A = b.A;
     const double* rp = ta.root_prior + (int64_t)t * A;
     int cur = 0, curN = T.root_N, depth = 0;
@@ -297,49 +390,51 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
     int leaf = -1;
     while (true) {
         char* np = node_ptr(ta, t, cur);
-        dbaz_state h = load_hdr(np);
-        Child c[APL];
-        const bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
-        if (interior) {
-            const Child* ch = node_children(np);
+        // header and child records are fetched together; an unexpanded / terminal node has garbage
+        // child records, which are loaded but never interpreted
+        const uint4* hp = reinterpret_cast<const uint4*>(np);
+        const uint4 h0 = hp[0], h1 = hp[1];
+        uint4 craw[APL];
 #pragma unroll
-            for (int k = 0; k < APL; ++k) {
-                int a = lane + 32 * k;
-                if (a < A) *reinterpret_cast<int4*>(&c[k]) = *reinterpret_cast<const int4*>(&ch[a]);
-            }
+        for (int k = 0; k < APL; ++k) {
+            int a = lane + 32 * k;
+            craw[k] = make_uint4(0, 0, 0, 0);
+            if (a < A) craw[k] = hp[2 + a];
         }
+        const double c0 = puct_c0(ta, curN);
+        double rprior[APL];
+        if (depth == 0) {
+#pragma unroll
+            for (int k = 0; k < APL; ++k) { int a = lane + 32 * k; rprior[k] = a < A ? rp[a] : 0.0; }
+        }
+        const Hdr h = unpack_hdr(h0, h1);
+        const bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
         if (depth == 0 && lane == 0) path[0] = PATH_ROOT | ((uint32_t)h.to_play << 31);
         if (!interior) { leaf = cur; leaf_hdr = h; break; }
 
-        Mask<NW> e = load_edges<NW>(h);
-        double c0 = puct_c0(ta, curN);
-        double sq = __dsqrt_rn((double)curN);
+        const Mask<NW> e = hdr_edges<NW>(h);
+        const double sq = __dsqrt_rn((double)curN);
         double best = -INFINITY;
         int best_a = 0x7fffffff;
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
-            int a = lane + 32 * k;
-            bool legal = la.real[k] && !mask_test(e, a < A ? a : 0);
+            const int a = lane + 32 * k;
+            const bool legal = la.real[k] && !mask_test(e, a < A ? a : 0);
             if (legal) {
-                int sign = la.closes(k, e, a) ? 1 : -1;
-                double prior = (depth == 0) ? rp[a] : (double)c[k].prior;
-                double sc = ucb_score<APL, NW>(c0, sq, c[k], prior, sign);
+                Child c;
+                c.W = __uint_as_float(craw[k].x); c.N = (int)craw[k].y; c.prior = __uint_as_float(craw[k].z);
+                const int sign = la.closes(k, e, a) ? 1 : -1;
+                const double prior = (depth == 0) ? rprior[k] : (double)c.prior;
+                const double sc = ucb_score<APL, NW>(c0, sq, c, prior, sign);
                 if (best_a == 0x7fffffff || sc > best) { best = sc; best_a = a; }
             }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, best, off);
-            int oa = __shfl_xor_sync(0xffffffffu, best_a, off);
-            bool take = (oa != 0x7fffffff) && (best_a == 0x7fffffff || ob > best || (ob == best && oa < best_a));
-            if (take) { best = ob; best_a = oa; }
-        }
-        const int a = best_a;  // a non-terminal node always has a legal move
+        const int a = warp_argmax(best, best_a);  // a non-terminal node always has a legal move
         const int owner = a & 31, kk = a >> 5;
         int child = 0, childN = 0, ncl = 0;
 #pragma unroll
         for (int k = 0; k < APL; ++k)
-            if (k == kk) { child = c[k].child; childN = c[k].N; ncl = la.closes(k, e, lane + 32 * k); }
+            if (k == kk) { child = (int)craw[k].w; childN = (int)craw[k].y; ncl = la.closes(k, e, lane + 32 * k); }
         child = __shfl_sync(0xffffffffu, child, owner);
         childN = __shfl_sync(0xffffffffu, childN, owner);
         ncl = __shfl_sync(0xffffffffu, ncl, owner);
@@ -348,17 +443,19 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
         if (lane == 0) path[depth] = ((uint32_t)cur << 8) | (uint32_t)a | ((uint32_t)child_tp << 31);
         if (child == 0) {
             // lazily create the child (mcts.py:53-54 -> BoxesState.play, dots_boxes_game.py:91-94)
-            int idx = T.n_nodes;
+            const int idx = T.n_nodes;
             if (idx >= ta.max_nodes) { T.flags |= TF_ERR_POOL; T.sims_left = 0; return 0; }
             T.n_nodes = idx + 1;
-            dbaz_state ns = h;
-            state_apply<NW>(ns, a, ncl);
-            int r = state_result(ns);
+            Hdr ns = h;
+            if (NW == 1 || a < 64) ns.e0 |= 1ull << (a & 63); else ns.e1 |= 1ull << (a & 63);
+            ns.just_played = h.to_play;
+            ns.to_play = child_tp;
+            if (ncl) { if (h.to_play) ns.btc1 -= 2 * ncl; else ns.btc0 -= 2 * ncl; }
+            const int r = hdr_result(ns);
             ns.flags = (r != DBAZ_RESULT_NONE) ? NF_TERMINAL : 0;
             ns.depth = h.depth + 1;
-            ns.parent = cur; ns.parent_action = (int16_t)a; ns.result = (int16_t)r;
-            char* cp = node_ptr(ta, t, idx);
-            if (lane == 0) store_hdr(cp, ns);
+            ns.parent = cur; ns.parent_action = a; ns.result = r;
+            if (lane == 0) store_hdr_regs(node_ptr(ta, t, idx), ns);
             if (lane == owner) node_children(np)[a].child = idx;
             leaf = idx; leaf_hdr = ns;
             break;
@@ -406,7 +503,7 @@ k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, cons
 }
 
 template <int APL, int NW>
-__global__ void __launch_bounds__(TREE_WARPS * 32)
+__global__ void __launch_bounds__(TREE_WARPS * 32, APL == 1 ? 7 : (APL == 2 ? 5 : 3))
 k_search_step(Board b, TreeArgs ta, const float* __restrict__ priors, const float* __restrict__ values,
               const double* __restrict__ noise, double coeff, void* __restrict__ planes, int dtype, int layout,
               dbaz_state* __restrict__ leaf_states, int8_t* __restrict__ leaf_kind) {
@@ -414,17 +511,27 @@ k_search_step(Board b, TreeArgs ta, const float* __restrict__ priors, const floa
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * TREE_WARPS + warp;
     if (t >= ta.n_trees) return;
+    // ---- one round trip: everything whose address depends only on t
     TreeRec T = ta.trees[t];
-    if (T.leaf < 0 && T.sims_left <= 0) {  // idle tree: nothing to read or write
+    StepInputs<APL> in;
+    in.lh0 = ta.leaf_hdr[2 * t]; in.lh1 = ta.leaf_hdr[2 * t + 1];
+#pragma unroll
+    for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? ta.path[(int64_t)t * PATH_CAP + lane + 32 * i] : 0u;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) { int a = lane + 32 * k; in.p[k] = a < b.A ? priors[(int64_t)t * b.A + a] : 0.0f; }
+    in.value = values[t];
+    LaneActions<APL, NW> la;
+    la.load(b, ta.act_tab, lane);
+
+    if (T.leaf < 0 && T.sims_left <= 0) {  // idle tree
         if (leaf_kind && lane == 0) leaf_kind[t] = 0;
         return;
     }
     double* sh = sh_all[warp];
     if (T.leaf >= 0) {
-        tree_expand_backup<APL, NW>(b, ta, t, T, priors, values, sh, lane);
-        // lane 0 owns the authoritative TreeRec; re-broadcast the fields the other lanes need
+        tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane);
+        // lane 0 owns the authoritative TreeRec; re-broadcast the field the other lanes need
         T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
-        T.leaf = -1;
         __syncwarp();
         if (T.flags & TF_PREP_PENDING) {
             dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
@@ -433,18 +540,22 @@ k_search_step(Board b, TreeArgs ta, const float* __restrict__ priors, const floa
     }
     int kind = 0;
     if (T.sims_left > 0) {
-        LaneActions<APL, NW> la;
-        la.init(b, lane);
-        dbaz_state lh;
+        Hdr lh;
         __syncwarp();  // backup stores above must be visible to the selection loads below
         kind = tree_select<APL, NW>(b, ta, t, T, la, lh, lane);
         if (kind) {
             T.sims_left -= 1;
-            write_planes_warp<NW>(b, lh, planes, t, dtype, layout, lane);
-            if (leaf_states && lane == 0) {
-                dbaz_state pub = lh;
-                pub.flags = 0; pub.depth = 0; pub.parent = -1; pub.parent_action = -1;
-                store_hdr(reinterpret_cast<char*>(&leaf_states[t]), pub);
+            const Mask<NW> e = hdr_edges<NW>(lh);
+            write_planes_warp<NW>(b, e, (int)(int8_t)(lh.to_play ? lh.btc1 : lh.btc0), planes, t, dtype, layout, lane);
+            if (lane == 0) {
+                uint4 a4, b4;
+                pack_hdr(lh, a4, b4);
+                ta.leaf_hdr[2 * t] = a4; ta.leaf_hdr[2 * t + 1] = b4;
+                if (leaf_states) {
+                    Hdr pub = lh;
+                    pub.flags = 0; pub.depth = 0; pub.parent = -1; pub.parent_action = -1;
+                    store_hdr_regs(reinterpret_cast<char*>(&leaf_states[t]), pub);
+                }
             }
         }
     }

@@ -190,6 +190,25 @@ class Engine:
         self._ck(self.lib.dbaz_fake_nn(self._h, _ptr(leaf_states), _ptr(priors), _ptr(values), int(kind), n, self._stream()))
         return priors, values
 
+    # ------------------------------------------------- leaf-eval fused stages
+    def nn_epilogue(self, x, bias, scale, shift, mode=0, res=None):
+        """In place on x ([..., channels] contiguous, channel innermost): mode 0 scale*relu(x+bias)+shift,
+        mode 1 relu(scale*(x+bias)+shift(+res)), mode 2 scale*(x+bias)+shift (include/dbaz_b200.h)."""
+        ch = x.shape[-1]
+        rows = x.numel() // ch
+        self._ck(self.lib.dbaz_nn_epilogue(self._h, _ptr(x), _ptr(res), _ptr(bias), _ptr(scale), _ptr(shift), rows, ch,
+                                           _DTYPE_CODE[x.dtype], int(mode), self._stream()))
+        return x
+
+    def nn_heads(self, logits, priors=None, values=None):
+        """logits [n, ld] (policy logits | value pre-activation | padding) -> softmax priors, tanh values (float32)."""
+        n, ld = logits.shape
+        priors = self.priors if priors is None else priors
+        values = self.values if values is None else values
+        self._ck(self.lib.dbaz_nn_heads(self._h, _ptr(logits), ld, _DTYPE_CODE[logits.dtype], _ptr(priors), _ptr(values), n,
+                                        self._stream()))
+        return priors, values
+
     # -------------------------------------------------------------- search
     def reset_roots(self, states=None):
         """create_root_uct_node (mcts.py:156-160) for every tree."""

@@ -236,3 +236,128 @@ class DeviceEvaluator:
         logp, v = self.model(eng.planes)
         torch.exp(logp.float(), out=eng.priors)  # nn.py:159: probabilities, float32
         eng.values.copy_(v.reshape(-1))
+
+
+def _bn_affine(bn):
+    """Eval-mode BatchNorm as y = scale*x + shift (float32)."""
+    scale = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps))
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class FusedSimpleNN:
+    """Inference plan for SimpleNN (dots_boxes_nn.py:61-98): cuDNN convs / cuBLAS GEMMs on NHWC tensors with
+    the engine's fused epilogue kernel (bias + ReLU + BN in one pass) between them, fc0's columns permuted to
+    the NHWC flatten order, policy and value heads as ONE GEMM whose softmax / tanh write the engine's
+    float32 buffers directly.  Same function as the module in eval mode up to rounding of the compute dtype."""
+
+    engine_launches = 8  # 7 epilogues + 1 heads kernel per wave
+
+    def __init__(self, model, engine, dtype=torch.bfloat16):
+        self.engine, self.dtype = engine, dtype
+        dev = engine.device
+        model = model.to(dev).train(False)
+        self.convs = []
+        for i in range(5):
+            conv, bn = getattr(model, f"conv{i}"), getattr(model, f"bn{i}")
+            w = conv.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last)
+            s, t = _bn_affine(bn)
+            self.convs.append((w, conv.bias.detach().float().contiguous(), s, t, conv.padding))
+        c_out, hh, ww = N_CH_OUT(model), engine.rows - 2, engine.cols - 2
+        w0 = model.fc0.weight.detach().view(-1, c_out, hh, ww).permute(0, 2, 3, 1).reshape(model.fc0.out_features, -1)
+        self.fcs = []
+        for w, lin, bn in ((w0, model.fc0, model.bn_fc0), (model.fc1.weight.detach(), model.fc1, model.bn_fc1)):
+            s, t = _bn_affine(bn)
+            self.fcs.append((w.to(dtype).t().contiguous(), lin.bias.detach().float().contiguous(), s, t))
+        A = engine.A
+        ld = (A + 1 + 7) // 8 * 8
+        wh = torch.zeros((ld, model.policy_fc.in_features), dtype=torch.float32, device=dev)
+        bh = torch.zeros((ld,), dtype=torch.float32, device=dev)
+        wh[:A] = model.policy_fc.weight.detach(); wh[A] = model.value_fc.weight.detach()[0]
+        bh[:A] = model.policy_fc.bias.detach(); bh[A] = model.value_fc.bias.detach()[0]
+        self.wh, self.bh = wh.to(dtype).t().contiguous(), bh.to(dtype)
+        engine.set_planes(dtype, channels_last=True)
+
+    @torch.no_grad()
+    def __call__(self, eng):
+        x = eng.planes
+        for w, b, s, t, pad in self.convs:
+            x = F.conv2d(x, w, None, padding=pad)
+            eng.nn_epilogue(x.permute(0, 2, 3, 1), b, s, t, mode=0)
+        x = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+        for w, b, s, t in self.fcs:
+            x = torch.mm(x, w)
+            eng.nn_epilogue(x, b, s, t, mode=0)
+        eng.nn_heads(torch.addmm(self.bh, x, self.wh))
+
+
+def N_CH_OUT(model):
+    return model.conv4.out_channels
+
+
+class FusedResNetZero:
+    """Inference plan for ResNetZero (nn.py:108-122): per conv one cuDNN call + one fused epilogue
+    (bias + BN + residual + ReLU); both 1x1 head convs as one conv, both head FCs as one GEMM."""
+
+    def __init__(self, model, engine, dtype=torch.bfloat16):
+        self.engine, self.dtype = engine, dtype
+        dev = engine.device
+        model = model.to(dev).train(False)
+        cl = torch.channels_last
+
+        def conv_pack(conv, bn):
+            if isinstance(conv, nn.Sequential):
+                raise NotImplementedError("even kernel sizes are not supported by the fused plan")
+            s, t = _bn_affine(bn)
+            return (conv.weight.detach().to(dtype).contiguous(memory_format=cl), conv.bias.detach().float().contiguous(), s, t,
+                    conv.padding)
+        s_in, t_in = _bn_affine(model.bn_input)
+        self.in_scale = s_in.view(1, -1, 1, 1).to(dtype)
+        self.in_shift = t_in.view(1, -1, 1, 1).to(dtype)
+        self.stem = conv_pack(model.resnet.conv0, model.resnet.bn0)
+        self.blocks = []
+        for blk in model.resnet.resblocks:
+            if blk.inner_conv is not None:
+                raise NotImplementedError("inner_channels is not supported by the fused plan")
+            self.blocks.append((conv_pack(blk.conv1, blk.bn1), conv_pack(blk.conv2, blk.bn2)))
+        ph, vh = model.policy_head, model.value_head
+        pw, pb, ps, pt, _ = conv_pack(ph.conv0, ph.bn0)
+        vw, vb, vs, vt, _ = conv_pack(vh.conv0, vh.bn0)
+        self.head_conv = (torch.cat([pw, vw], 0).contiguous(memory_format=cl), torch.cat([pb, vb]), torch.cat([ps, vs]),
+                          torch.cat([pt, vt]))
+        cp, cv = pw.shape[0], vw.shape[0]
+        hw = engine.rows * engine.cols
+        A, fi = engine.A, vh.fc0.out_features
+        # one GEMM over the NHWC-flattened [hw, cp+cv] head activations: columns [0, A) policy logits, [A, A+fi) value hidden
+        W = torch.zeros((hw, cp + cv, A + fi), dtype=torch.float32, device=dev)
+        W[:, :cp, :A] = ph.fc.weight.detach().view(A, cp, hw).permute(2, 1, 0)
+        W[:, cp:, A:] = vh.fc0.weight.detach().view(fi, cv, hw).permute(2, 1, 0)
+        self.head_w = W.reshape(hw * (cp + cv), A + fi).to(dtype).contiguous()
+        self.head_b = torch.cat([ph.fc.bias.detach(), vh.fc0.bias.detach()]).to(dtype)
+        self.v_w = vh.fc1.weight.detach().to(dtype).t().contiguous()
+        self.v_b = vh.fc1.bias.detach().to(dtype)
+        self.A = A
+        self.ld = (A + 1 + 7) // 8 * 8
+        self.logits = torch.zeros((engine.n_games, self.ld), dtype=dtype, device=dev)
+        self.engine_launches = 2 + 2 * len(self.blocks) + 2
+        engine.set_planes(dtype, channels_last=True)
+
+    @torch.no_grad()
+    def __call__(self, eng):
+        x = eng.planes * self.in_scale + self.in_shift
+        w, b, s, t, pad = self.stem
+        x = F.conv2d(x, w, None, padding=pad)
+        eng.nn_epilogue(x.permute(0, 2, 3, 1), b, s, t, mode=1)
+        for (w1, b1, s1, t1, p1), (w2, b2, s2, t2, p2) in self.blocks:
+            y = F.conv2d(x, w1, None, padding=p1)
+            eng.nn_epilogue(y.permute(0, 2, 3, 1), b1, s1, t1, mode=1)
+            y = F.conv2d(y, w2, None, padding=p2)
+            eng.nn_epilogue(y.permute(0, 2, 3, 1), b2, s2, t2, mode=1, res=x.permute(0, 2, 3, 1))
+            x = y
+        hw_, hb, hs, ht = self.head_conv
+        h = F.conv2d(x, hw_, None)
+        eng.nn_epilogue(h.permute(0, 2, 3, 1), hb, hs, ht, mode=1)
+        out = torch.addmm(self.head_b, h.permute(0, 2, 3, 1).reshape(h.shape[0], -1), self.head_w)
+        self.logits[:, :self.A] = out[:, :self.A]
+        self.logits[:, self.A:self.A + 1] = torch.addmm(self.v_b, F.relu(out[:, self.A:]), self.v_w)
+        eng.nn_heads(self.logits)

@@ -140,6 +140,20 @@ int dbaz_search_advance_roots(dbaz_engine *e, const int32_t *moves, int32_t reus
  * last_error) if any tree faulted. */
 int dbaz_search_status(dbaz_engine *e, int64_t *out8, uint64_t stream);
 
+/* ---- leaf-evaluation pipeline: fused elementwise stages between the library GEMMs/convs ----
+ * (replaces the separate bias / ReLU / eval-BatchNorm / softmax passes of NeuralNetWrapper.predict_sync,
+ * nn.py:155-160, around dots_boxes_nn.py:85-98 and nn.py:49-58).  x: [rows, channels], channel innermost
+ * (NHWC conv output or linear output), updated in place; bias may be NULL; scale/shift are the folded
+ * eval-mode BatchNorm (gamma/sqrt(var+eps), beta - mean*scale), float32[channels].
+ *   mode 0: y = scale*relu(x+bias)+shift      mode 1: y = relu(scale*(x+bias)+shift (+res))
+ *   mode 2: y = scale*(x+bias)+shift */
+int dbaz_nn_epilogue(dbaz_engine *e, void *x, const void *res, const float *bias, const float *scale, const float *shift,
+                     int64_t rows, int32_t channels, int32_t dtype, int32_t mode, uint64_t stream);
+/* logits [n][ld]: columns 0..A-1 policy logits, column A value pre-activation ->
+ * priors float32[n][A] = softmax (exp(log_softmax)), values float32[n] = tanh. */
+int dbaz_nn_heads(dbaz_engine *e, const void *logits, int32_t ld, int32_t dtype, float *priors, float *values, int64_t n,
+                  uint64_t stream);
+
 /* ---- test/bench utility: deterministic stand-in for the policy/value net ----
  * (SURVEY.md 8a KAT definition; kind 0 hash-seeded, kind 1 uniform prior) over leaf_states[n]. */
 int dbaz_fake_nn(dbaz_engine *e, const dbaz_state *leaf_states, float *priors, float *values, int32_t kind,

@@ -1,0 +1,69 @@
+"""GPU numerics of the leaf-evaluation pipeline: fused inference plans (library convs/GEMMs + the
+engine's fused epilogue / heads kernels) against the plain PyTorch fp32 modules in eval mode.
+Tolerances: fp32 plan 2e-5 abs on probabilities/values (north_star: Q/priors within 1e-5 relative is
+for the TREE given identical net outputs; the net itself is floating point and its plan re-associates
+sums); bf16 plan 3e-2 abs (bf16 has 8 mantissa bits)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _randomise_bn(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.3)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+
+
+@pytest.mark.parametrize("net,board", [("simple", (3, 3)), ("simple", (5, 5)), ("resnet", (3, 3)), ("resnet", (5, 5))])
+def test_fused_plans_match_torch_modules(net, board):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dotsboxesaz_b200 import engine
+    from dotsboxesaz_b200.nn import (DeviceEvaluator, FusedResNetZero, FusedSimpleNN, ResNetZero, resnet_zero_parameters)
+    from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
+    from dotsboxesaz_b200.utils.utils import DotDict
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n = 512
+    eng = engine.Engine(board, n_games=n, max_nodes=64)
+    torch.manual_seed(1)
+    if net == "simple":
+        model = SimpleNN(board=board)
+        plan_cls = FusedSimpleNN
+    else:
+        model = ResNetZero(DotDict({"nn": {"model_parameters": resnet_zero_parameters(board, nb_blocks=4)}}))
+        plan_cls = FusedResNetZero
+    _randomise_bn(model, 2)
+    model = model.cuda().eval()
+    # leaves of a real search as inputs
+    st = eng.new_states(n)
+    plies, _ = eng.random_rollout(st.clone(), seed=3, record_moves=True)
+    for ply in range(6):
+        legal = eng.valid_moves(st).float()
+        mv = torch.multinomial(legal + 1e-9, 1).reshape(-1).int()
+        eng.play(st, torch.where(torch.arange(n, device=st.device) % 7 > ply, mv, torch.full_like(mv, -1)))
+    x32 = eng.features(st, torch.float32)
+    with torch.no_grad():
+        logp, v = model(x32)
+    p_ref, v_ref = torch.exp(logp), v.reshape(-1)
+    for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 3e-2)):
+        plan = plan_cls(model, eng, dtype=dtype)
+        eng.planes.copy_(x32.to(dtype))
+        plan(eng)
+        torch.cuda.synchronize()
+        assert torch.isfinite(eng.priors).all()
+        assert (eng.priors.sum(1) - 1).abs().max() < 1e-3
+        assert (eng.priors - p_ref).abs().max().item() < tol, (net, board, dtype, (eng.priors - p_ref).abs().max().item())
+        assert (eng.values - v_ref).abs().max().item() < tol * (1 if dtype == torch.float32 else 3)
+        # the un-fused evaluator (plain module on the same planes) must agree too
+        ev = DeviceEvaluator(model, eng, dtype=dtype, channels_last=True)
+        eng.planes.copy_(x32.to(dtype))
+        ev(eng)
+        assert (eng.priors - p_ref).abs().max().item() < tol
+    eng.close()
