@@ -62,3 +62,10 @@ def elo_rating2(elo0, elo1, n0, n1, K=30):
     p1 = _expected(elo0, elo1)
     p0 = 1 - p1
     return elo0 + K * (n0 * p1 - n1 * p0), elo1 + K * (n1 * p0 - n0 * p1)
+
+
+def write_to_hdf(hdf_file, key, dataframe):
+    """utils/utils.py:94-96: append the sample rows to table `key` of the HDF store (needs pytables)."""
+    import pandas as pd
+    with pd.HDFStore(hdf_file, mode="a") as store:
+        store.append(key, dataframe, format="table")

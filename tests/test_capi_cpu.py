@@ -1,0 +1,102 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dbaz_b200.h declares; host logic that
+needs no GPU (configs, Elo, sharding); the engine fails loudly without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "dbaz_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dbaz_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dotsboxesaz_b200 import _capi
+    lib = _capi.load()
+    names = _declared()
+    assert len(names) >= 25
+    assert sorted(_capi.SYMBOLS) == names, set(names) ^ set(_capi.SYMBOLS)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.dbaz_abi_version() == 1
+    assert lib.dbaz_sizeof_state() == 32 == _capi.STATE_DTYPE.itemsize
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dotsboxesaz_b200 import _capi, engine
+    with pytest.raises(RuntimeError):
+        engine.Engine((3, 3), n_games=4)
+    lib = _capi.load()
+    cfg = _capi.Config(1, 0, 3, 3, 4, 16, 0, 0, 1.25, 19652.0)
+    h = ctypes.c_void_p()
+    assert lib.dbaz_engine_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert b"no CUDA device" in lib.dbaz_last_error(None)
+    bad = _capi.Config(1, 0, 9, 9, 4, 16, 0, 0, 1.25, 19652.0)
+    assert lib.dbaz_engine_create(ctypes.byref(bad), ctypes.byref(h)) != 0
+    assert b"too large" in lib.dbaz_last_error(None)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dotsboxesaz_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("# oracle", ""), (dirpath, f)
+
+
+def test_dotdict_and_elo():
+    from dotsboxesaz_b200.utils.utils import DictWithDefault, DotDict, elo_rating2
+    d = DotDict({"a": {"b": 1, "s": "x/_exp_/y"}, "c": 2})
+    assert d.a.b == 1 and d.missing is None
+    d.merge({"a": {"b": 3, "z": {"q": 1}}, "e": 5})
+    assert d.a.b == 3 and d.a.z.q == 1 and d.e == 5 and d.a.s == "x/_exp_/y"
+    d.rewrite_str("_exp_", "run1")
+    assert d.a.s == "x/run1/y"
+    d.k = {"n": 1}
+    assert isinstance(d.k, DotDict) and d.k.n == 1
+    calls = []
+    dd = DictWithDefault(lambda k: calls.append(k) or k * 2)
+    assert dd[3] == 6 and dd[3] == 6 and calls == [3]
+    e0, e1 = elo_rating2(1200, 1200, 12, 8, K=30)
+    assert abs(e0 - 1260) < 1e-9 and abs(e1 - 1140) < 1e-9
+
+
+def test_shard_game_indices_partition():
+    from dotsboxesaz_b200.self_play import shard_game_indices
+    for n, w in ((10, 1), (10, 3), (4096, 8), (5, 8)):
+        parts = [shard_game_indices(n, r, w) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_dataset_frame_matches_reference_columns():
+    """_dataset builds the DataFrame of self_play.py:95-156 (columns, dtypes, MultiIndex)."""
+    from dotsboxesaz_b200.self_play import _dataset
+    from golden_io import load
+    G = load("selfplay")[0]
+    cols = G["columns"]
+    rows = []
+    ref = np.array(G["rows"], dtype=np.float64)
+    ix = {c: i for i, c in enumerate(cols)}
+    for r in ref:
+        rows.append({"game_idx": int(r[ix["game_idx"]]), "move_idx": int(r[ix["move_idx"]]),
+                     "move": None if r[ix["move"]] < 0 else int(r[ix["move"]]), "player": int(r[ix["player"]]),
+                     "features": r[[ix[c] for c in cols if c.startswith("x_")]].astype(np.int16),
+                     "pi": r[[ix[c] for c in cols if c.startswith("pi_")]], "z": r[ix["z"]],
+                     "stats": (int(r[ix["max_deepness"]]), int(r[ix["tree_size"]]), int(r[ix["terminal_count"]]),
+                               np.float32(r[ix["q_value"]]))})
+    df = _dataset(rows, 3, True)
+    assert df.index.names == ["generation", "game_idx", "move_idx"]
+    assert str(df["move"].dtype) == "int16" and str(df["player"].dtype) == "int8" and str(df["q_value"].dtype) == "float32"
+    flat = df.reset_index()
+    assert list(flat.columns) == cols
+    assert np.array_equal(flat.to_numpy(dtype=np.float64), ref)
