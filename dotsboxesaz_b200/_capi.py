@@ -51,6 +51,7 @@ SYMBOLS = {
     "dbaz_search_advance_roots": (C.c_int, [_P, _P, _I32, _U64]),
     "dbaz_search_status": (C.c_int, [_P, _P, _U64]),
     "dbaz_nn_epilogue": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _U64]),
+    "dbaz_nn_stem": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I64, _U64]),
     "dbaz_nn_heads": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _I64, _U64]),
     "dbaz_fake_nn": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _U64]),
 }

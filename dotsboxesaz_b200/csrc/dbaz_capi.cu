@@ -82,6 +82,30 @@ int launch_ok(dbaz_engine* e, const char* what) {
         else { constexpr int APL = 4, NW = 2; EXPR; }            \
     } while (0)
 
+template <typename T>
+static int launch_stem(dbaz_engine* e, const dbaz_state* leaves, const float* w01, const float* Bp, const float* K2,
+                       const float* scale, const float* shift, T* out, int n, int cout, int mode, cudaStream_t st) {
+    const int H = e->board.rows, W = e->board.cols;
+    const int groups = cout / 8, per_block = 128 / groups;
+    const size_t smem = (size_t)((18 + 2 * H * W) * cout + 2 * cout) * sizeof(float);
+    const int resident = std::max(1, (int)std::min<size_t>(4, (200 * 1024) / smem));
+    const int grid = std::max(1, std::min((n + per_block - 1) / per_block, e->n_sms * resident));
+#define DBAZ_STEM(HH, WW)                                                                                               \
+    if (H == HH && W == WW) {                                                                                           \
+        cudaFuncSetAttribute(k_nn_stem<T, HH, WW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        cudaFuncSetAttribute(k_nn_stem<T, HH, WW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        if (mode == 0) k_nn_stem<T, HH, WW, 0><<<grid, 128, smem, st>>>(leaves, w01, Bp, K2, scale, shift, out, n, cout); \
+        else k_nn_stem<T, HH, WW, 1><<<grid, 128, smem, st>>>(leaves, w01, Bp, K2, scale, shift, out, n, cout);          \
+        return launch_ok(e, "k_nn_stem");                                                                               \
+    }
+    DBAZ_STEM(4, 4)
+    DBAZ_STEM(6, 6)
+    DBAZ_STEM(3, 3)
+    DBAZ_STEM(5, 5)
+#undef DBAZ_STEM
+    return fail(e, "dbaz_nn_stem: no specialisation for this board size (3x3, 5x5, 2x2, 4x4 boxes are built)");
+}
+
 extern "C" {
 
 int dbaz_abi_version(void) { return DBAZ_ABI_VERSION; }
@@ -307,6 +331,19 @@ int dbaz_nn_epilogue(dbaz_engine* e, void* x, const void* res, const float* bias
     }
 #undef DBAZ_EPI
     return launch_ok(e, "k_nn_epilogue");
+}
+
+int dbaz_nn_stem(dbaz_engine* e, const dbaz_state* leaf_states, const float* w01, const float* bias_pos, const float* k2_pos,
+                 const float* scale, const float* shift, void* out, int32_t cout, int32_t dtype, int32_t mode, int64_t n,
+                 uint64_t stream) {
+    if (!e || !leaf_states || !w01 || !bias_pos || !k2_pos || !scale || !shift || !out) return 1;
+    if (n <= 0) return 0;
+    if (cout < 8 || cout > 256 || (cout & (cout - 1))) return fail(e, "dbaz_nn_stem: cout must be a power of two in [8, 256]");
+    if (mode < 0 || mode > 1) return fail(e, "bad stem mode");
+    DeviceGuard guard(e->cfg.device);
+    if (dtype == DBAZ_BF16) return launch_stem<__nv_bfloat16>(e, leaf_states, w01, bias_pos, k2_pos, scale, shift, (__nv_bfloat16*)out, (int)n, cout, mode, S(stream));
+    if (dtype == DBAZ_F16) return launch_stem<__half>(e, leaf_states, w01, bias_pos, k2_pos, scale, shift, (__half*)out, (int)n, cout, mode, S(stream));
+    return fail(e, "dbaz_nn_stem: 16-bit output types only");
 }
 
 int dbaz_nn_heads(dbaz_engine* e, const void* logits, int32_t ld, int32_t dtype, float* priors, float* values, int64_t n,

@@ -159,3 +159,146 @@ __global__ void k_nn_heads(const T* __restrict__ logits, int ld, int A, float* _
 }
 
 }  // namespace dbaz
+
+namespace dbaz {
+
+// ---------------------------------------------------------------------------------------------
+// Stem: leaf gather + first 3x3 convolution + epilogue in ONE kernel, straight from the packed
+// 32-byte leaf states (no plane tensor, no library call, no padding / cast / bias / ReLU / BN passes).
+//
+// The input planes of a leaf are two bit planes (edges) and one constant plane k = 2*boxes_to_close
+// (dots_boxes_game.py:96-100), so with zero padding the convolution is, per output position p and
+// channel co,
+//     y[p][co] = B[p][co] + k * K2[p][co] + sum over (plane c in {0,1}, tap inside the board, edge bit set) W01[c][tap][co]
+// where the host has folded into B / K2 / W01 (all float32, exact algebra): the conv bias, the optional
+// input BatchNorm of ResNetZero (nn.py:118; its shift only contributes through in-board taps, hence the
+// position dependence) and the third plane's weights summed over in-board taps.  The epilogue is the
+// same as k_nn_epilogue (mode 0: scale*relu(y)+shift; mode 1: relu(scale*y+shift)).
+//
+// Thread = (leaf, group of 8 output channels); all positions of a tile are accumulated in registers
+// with the tap loop outermost, so each weight vector is read from shared memory once per leaf.  H, W
+// are template parameters: every in-board test and bit index is a compile-time constant and padded
+// taps cost nothing (31 % of a 4x4 map).  Output: [n][H][W][cout] (NHWC), 16-byte stores, a warp
+// writes 512 contiguous bytes per position when cout == 256.
+template <typename T, int H, int W, int MODE, int P0, int PN>
+__device__ __noinline__ void stem_tile(const uint64_t e0, const uint64_t e1, const float kf, const float* __restrict__ w_s,
+                                       const float* __restrict__ b_s, const float* __restrict__ k_s, const float* __restrict__ sc_s,
+                                       const float* __restrict__ sh_s, T* __restrict__ out_leaf, int cout, int c0) {
+    const int g = c0 >> 3, half4 = cout >> 3;  // swizzled shared layout, see k_nn_stem
+    // the (up to 3 rows x W cols x 2 planes) input cells this tile touches, as 0.0f / 1.0f in registers;
+    // indices are compile-time constants, unused entries are eliminated
+    constexpr int R0 = (P0 / W) - 1, R1 = ((P0 + PN - 1) / W) + 1;  // row range touched (may fall outside the board)
+    constexpr int NR = R1 - R0 + 1;
+    float xv[2][NR][W];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int x = 0; x < W; ++x) {
+                const int hh = R0 + r;
+                if (hh < 0 || hh >= H) { xv[c][r][x] = 0.0f; continue; }
+                const int a = c * H * W + hh * W + x;
+                const uint64_t bit = ((a < 64 ? e0 : e1) >> (a & 63)) & 1ull;
+                xv[c][r][x] = __uint_as_float((unsigned)bit * 0x3f800000u);
+            }
+    float acc[PN][8];
+#pragma unroll
+    for (int p = 0; p < PN; ++p) {
+        const float4* b4 = reinterpret_cast<const float4*>(b_s + (size_t)(P0 + p) * cout) + g;
+        const float4* k4 = reinterpret_cast<const float4*>(k_s + (size_t)(P0 + p) * cout) + g;
+        const float4 b0 = b4[0], b1 = b4[half4], k0 = k4[0], k1 = k4[half4];
+        acc[p][0] = fmaf(kf, k0.x, b0.x); acc[p][1] = fmaf(kf, k0.y, b0.y); acc[p][2] = fmaf(kf, k0.z, b0.z); acc[p][3] = fmaf(kf, k0.w, b0.w);
+        acc[p][4] = fmaf(kf, k1.x, b1.x); acc[p][5] = fmaf(kf, k1.y, b1.y); acc[p][6] = fmaf(kf, k1.z, b1.z); acc[p][7] = fmaf(kf, k1.w, b1.w);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                asm volatile("" ::: "memory");  // keep one tap's weights live at a time
+                const float4* wv = reinterpret_cast<const float4*>(w_s + (size_t)((c * 3 + ky) * 3 + kx) * cout) + g;
+                const float4 w0 = wv[0], w1 = wv[half4];
+#pragma unroll
+                for (int p = 0; p < PN; ++p) {
+                    const int h = (P0 + p) / W, x = (P0 + p) % W;
+                    const int hh = h + ky - 1, ww = x + kx - 1;
+                    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;  // compile-time: padded taps cost nothing
+                    const float xin = xv[c][hh - R0][ww];
+                    acc[p][0] = fmaf(xin, w0.x, acc[p][0]); acc[p][1] = fmaf(xin, w0.y, acc[p][1]);
+                    acc[p][2] = fmaf(xin, w0.z, acc[p][2]); acc[p][3] = fmaf(xin, w0.w, acc[p][3]);
+                    acc[p][4] = fmaf(xin, w1.x, acc[p][4]); acc[p][5] = fmaf(xin, w1.y, acc[p][5]);
+                    acc[p][6] = fmaf(xin, w1.z, acc[p][6]); acc[p][7] = fmaf(xin, w1.w, acc[p][7]);
+                }
+            }
+    const float4* s4 = reinterpret_cast<const float4*>(sc_s) + g;
+    const float4* t4 = reinterpret_cast<const float4*>(sh_s) + g;
+    const float4 sa = s4[0], sb = s4[half4], ta = t4[0], tb = t4[half4];
+    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w}, sh[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+    for (int p = 0; p < PN; ++p) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = (MODE == 0) ? fmaf(sc[j], fmaxf(acc[p][j], 0.0f), sh[j]) : fmaxf(fmaf(sc[j], acc[p][j], sh[j]), 0.0f);
+        Vec8<T> v;
+        v.pack(y);
+        *reinterpret_cast<uint4*>(out_leaf + (size_t)(P0 + p) * cout + c0) = v.raw;
+    }
+}
+
+// Persistent CTAs of 128 threads: the folded weights, both position tables and the epilogue parameters live in
+// shared memory for the whole kernel; work is strided at leaf granularity (a group of cout/8 threads per leaf).
+template <typename T, int H, int W, int MODE>
+__global__ void __launch_bounds__(128, 4)
+k_nn_stem(const dbaz_state* __restrict__ leaves, const float* __restrict__ w01 /*[18][cout]*/, const float* __restrict__ Bp /*[H*W][cout]*/,
+          const float* __restrict__ K2 /*[H*W][cout]*/, const float* __restrict__ scale, const float* __restrict__ shift,
+          T* __restrict__ out, int n, int cout) {
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int HW = H * W, TILE = (W <= 4 ? 2 * W : W);  // whole rows per tile
+    float* w_s = smem_f;                 // [18][cout]
+    float* b_s = w_s + 18 * cout;        // [HW][cout]
+    float* k_s = b_s + HW * cout;        // [HW][cout]
+    float* sc_s = k_s + HW * cout;       // [cout]
+    float* sh_s = sc_s + cout;           // [cout]
+    {   // table fill with 16-byte loads, 8 in flight per thread (scalar loads made this the whole kernel's cost).
+        // Shared layout per row of `cout` floats: [half][group][4] -- a thread's channels 8g..8g+3 and 8g+4..8g+7 sit in
+        // two planes so that each of its two LDS.128 is stride-16-bytes across the warp (conflict-free); the natural
+        // layout puts lanes g and g+4 on the same banks.
+        auto fill = [&](float* dst, const float* src, int count) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            const int n4 = count >> 2, row4 = cout >> 2, half4 = cout >> 3;
+#pragma unroll 8
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                const int row = i / row4, q = i - row * row4;  // q-th float4 of the row: channels 4q..4q+3
+                d4[row * row4 + (q & 1) * half4 + (q >> 1)] = __ldg(s4 + i);
+            }
+        };
+        fill(w_s, w01, 18 * cout);
+        fill(b_s, Bp, HW * cout);
+        fill(k_s, K2, HW * cout);
+        fill(sc_s, scale, cout);
+        fill(sh_s, shift, cout);
+    }
+    __syncthreads();
+    const int groups = cout >> 3, per_block = blockDim.x / groups;
+    const int g = threadIdx.x % groups, c0 = g << 3;
+    for (int leaf = blockIdx.x * per_block + threadIdx.x / groups; leaf < n; leaf += gridDim.x * per_block) {
+        const uint4 s0 = reinterpret_cast<const uint4*>(leaves + leaf)[0];
+        const uint4 s1 = reinterpret_cast<const uint4*>(leaves + leaf)[1];
+        const uint64_t e0 = (uint64_t)s0.x | ((uint64_t)s0.y << 32), e1 = (uint64_t)s0.z | ((uint64_t)s0.w << 32);
+        const int to_play = s1.y & 0xffu;
+        const int btc = to_play ? (int)(int16_t)(s1.x >> 16) : (int)(int16_t)(s1.x & 0xffffu);
+        const float kf = (float)(int)(int8_t)btc;  // np.full_like(..., dtype=np.int8)
+        T* o = out + (size_t)leaf * HW * cout;
+#define DBAZ_STEM_TILE(I)                                                                                      \
+        if constexpr (HW > (I) * TILE)                                                                           \
+            stem_tile<T, H, W, MODE, (I) * TILE, (HW - (I) * TILE < TILE ? HW - (I) * TILE : TILE)>(e0, e1, kf, w_s, b_s, k_s, sc_s, sh_s, o, cout, c0);
+        DBAZ_STEM_TILE(0) DBAZ_STEM_TILE(1) DBAZ_STEM_TILE(2) DBAZ_STEM_TILE(3) DBAZ_STEM_TILE(4) DBAZ_STEM_TILE(5)
+#undef DBAZ_STEM_TILE
+        static_assert(HW <= 6 * TILE, "position tiles");
+    }
+}
+
+}  // namespace dbaz

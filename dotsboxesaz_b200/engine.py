@@ -200,6 +200,14 @@ class Engine:
                                            _DTYPE_CODE[x.dtype], int(mode), self._stream()))
         return x
 
+    def nn_stem(self, leaf_states, w01, bias_pos, k2_pos, scale, shift, out, mode=0):
+        """Leaf gather + first 3x3 conv + epilogue in one kernel, from packed states (include/dbaz_b200.h).
+        out: [n, L+1, C+1, cout] contiguous (NHWC), bf16/fp16."""
+        n, cout = leaf_states.shape[0], out.shape[-1]
+        self._ck(self.lib.dbaz_nn_stem(self._h, _ptr(leaf_states), _ptr(w01), _ptr(bias_pos), _ptr(k2_pos), _ptr(scale),
+                                       _ptr(shift), _ptr(out), cout, _DTYPE_CODE[out.dtype], int(mode), n, self._stream()))
+        return out
+
     def nn_heads(self, logits, priors=None, values=None):
         """logits [n, ld] (policy logits | value pre-activation | padding) -> softmax priors, tanh values (float32)."""
         n, ld = logits.shape

@@ -245,20 +245,43 @@ def _bn_affine(bn):
     return scale.contiguous(), shift.contiguous()
 
 
+def _stem_tables(conv, rows, cols, in_scale=None, in_shift=None):
+    """Host-side folding for Engine.nn_stem (float32, exact algebra): the conv over the three input planes
+    becomes  y[p] = B[p] + k*K2[p] + sum over set edge bits of W01[c][tap]  -- see dbaz_nn_kernels.cuh."""
+    w = conv.weight.detach().float()                       # [cout, 3, 3, 3]
+    dev = w.device
+    s = torch.ones(3, device=dev) if in_scale is None else in_scale.float()
+    t = torch.zeros(3, device=dev) if in_shift is None else in_shift.float()
+    ws = w * s.view(1, 3, 1, 1)
+    pad = conv.padding
+    e2 = torch.zeros((1, 3, rows, cols), device=dev); e2[0, 2] = 1.0
+    k2 = F.conv2d(e2, ws, None, padding=pad)[0]            # [cout, H, W]: plane-2 weights summed over in-board taps
+    tmap = t.view(1, 3, 1, 1).expand(1, 3, rows, cols).contiguous()
+    b = conv.bias.detach().float().view(-1, 1, 1) + F.conv2d(tmap, w, None, padding=pad)[0]
+    w01 = ws[:, :2].permute(1, 2, 3, 0).reshape(18, -1).contiguous()          # [c][ky][kx][cout]
+    to_pos = lambda x: x.permute(1, 2, 0).reshape(rows * cols, -1).contiguous()  # [H*W][cout]
+    return w01, to_pos(b), to_pos(k2)
+
+
 class FusedSimpleNN:
     """Inference plan for SimpleNN (dots_boxes_nn.py:61-98): cuDNN convs / cuBLAS GEMMs on NHWC tensors with
     the engine's fused epilogue kernel (bias + ReLU + BN in one pass) between them, fc0's columns permuted to
     the NHWC flatten order, policy and value heads as ONE GEMM whose softmax / tanh write the engine's
     float32 buffers directly.  Same function as the module in eval mode up to rounding of the compute dtype."""
 
-    engine_launches = 8  # 7 epilogues + 1 heads kernel per wave
+    engine_launches = 8  # stem + 6 epilogues + 1 heads kernel per wave
 
-    def __init__(self, model, engine, dtype=torch.bfloat16):
+    def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True):
         self.engine, self.dtype = engine, dtype
         dev = engine.device
         model = model.to(dev).train(False)
         self.convs = []
-        for i in range(5):
+        self.stem = None
+        if use_stem and dtype in (torch.bfloat16, torch.float16) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5)):
+            s0, t0 = _bn_affine(model.bn0)
+            self.stem = _stem_tables(model.conv0, engine.rows, engine.cols) + (s0, t0)
+            self.stem_out = torch.empty((engine.n_games, engine.rows, engine.cols, model.conv0.out_channels), dtype=dtype, device=dev)
+        for i in range(1 if self.stem is not None else 0, 5):
             conv, bn = getattr(model, f"conv{i}"), getattr(model, f"bn{i}")
             w = conv.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last)
             s, t = _bn_affine(bn)
@@ -280,7 +303,11 @@ class FusedSimpleNN:
 
     @torch.no_grad()
     def __call__(self, eng):
-        x = eng.planes
+        if self.stem is not None:
+            w01, bp, k2, s0, t0 = self.stem
+            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out, mode=0).permute(0, 3, 1, 2)
+        else:
+            x = eng.planes
         for w, b, s, t, pad in self.convs:
             x = F.conv2d(x, w, None, padding=pad)
             eng.nn_epilogue(x.permute(0, 2, 3, 1), b, s, t, mode=0)
@@ -299,7 +326,7 @@ class FusedResNetZero:
     """Inference plan for ResNetZero (nn.py:108-122): per conv one cuDNN call + one fused epilogue
     (bias + BN + residual + ReLU); both 1x1 head convs as one conv, both head FCs as one GEMM."""
 
-    def __init__(self, model, engine, dtype=torch.bfloat16):
+    def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True):
         self.engine, self.dtype = engine, dtype
         dev = engine.device
         model = model.to(dev).train(False)
@@ -315,6 +342,12 @@ class FusedResNetZero:
         self.in_scale = s_in.view(1, -1, 1, 1).to(dtype)
         self.in_shift = t_in.view(1, -1, 1, 1).to(dtype)
         self.stem = conv_pack(model.resnet.conv0, model.resnet.bn0)
+        self.fused_stem = None
+        c0 = model.resnet.conv0
+        if (use_stem and dtype in (torch.bfloat16, torch.float16) and not isinstance(c0, nn.Sequential) and c0.padding == (1, 1)
+                and c0.out_channels in (8, 16, 32, 64, 128, 256) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5))):
+            self.fused_stem = _stem_tables(c0, engine.rows, engine.cols, s_in, t_in) + (self.stem[2], self.stem[3])
+            self.stem_out = torch.empty((engine.n_games, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
         self.blocks = []
         for blk in model.resnet.resblocks:
             if blk.inner_conv is not None:
@@ -344,10 +377,14 @@ class FusedResNetZero:
 
     @torch.no_grad()
     def __call__(self, eng):
-        x = eng.planes * self.in_scale + self.in_shift
-        w, b, s, t, pad = self.stem
-        x = F.conv2d(x, w, None, padding=pad)
-        eng.nn_epilogue(x.permute(0, 2, 3, 1), b, s, t, mode=1)
+        if self.fused_stem is not None:
+            w01, bp, k2, s0, t0 = self.fused_stem
+            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out, mode=1).permute(0, 3, 1, 2)
+        else:
+            x = eng.planes * self.in_scale + self.in_shift
+            w, b, s, t, pad = self.stem
+            x = F.conv2d(x, w, None, padding=pad)
+            eng.nn_epilogue(x.permute(0, 2, 3, 1), b, s, t, mode=1)
         for (w1, b1, s1, t1, p1), (w2, b2, s2, t2, p2) in self.blocks:
             y = F.conv2d(x, w1, None, padding=p1)
             eng.nn_epilogue(y.permute(0, 2, 3, 1), b1, s1, t1, mode=1)

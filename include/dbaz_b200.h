@@ -149,6 +149,15 @@ int dbaz_search_status(dbaz_engine *e, int64_t *out8, uint64_t stream);
  *   mode 2: y = scale*(x+bias)+shift */
 int dbaz_nn_epilogue(dbaz_engine *e, void *x, const void *res, const float *bias, const float *scale, const float *shift,
                      int64_t rows, int32_t channels, int32_t dtype, int32_t mode, uint64_t stream);
+/* Leaf gather + first 3x3 conv (zero padding 1, 3 input planes) + epilogue in one kernel, reading the packed
+ * leaf states instead of a plane tensor (dots_boxes_game.py:96-100 + dots_boxes_nn.py:85 / nn.py:118-119,27-28).
+ * w01 float32[2][3][3][cout]: weights of the two edge planes; bias_pos / k2_pos float32[(L+1)*(C+1)][cout]:
+ * position-dependent constant and coefficient of the third plane's value (host-folded: conv bias, in-board
+ * taps of plane 2, optional input BatchNorm).  out [n][L+1][C+1][cout] (NHWC) bf16/fp16.
+ * mode 0: scale*relu(y)+shift, mode 1: relu(scale*y+shift). */
+int dbaz_nn_stem(dbaz_engine *e, const dbaz_state *leaf_states, const float *w01, const float *bias_pos, const float *k2_pos,
+                 const float *scale, const float *shift, void *out, int32_t cout, int32_t dtype, int32_t mode, int64_t n,
+                 uint64_t stream);
 /* logits [n][ld]: columns 0..A-1 policy logits, column A value pre-activation ->
  * priors float32[n][A] = softmax (exp(log_softmax)), values float32[n] = tanh. */
 int dbaz_nn_heads(dbaz_engine *e, const void *logits, int32_t ld, int32_t dtype, float *priors, float *values, int64_t n,

@@ -55,12 +55,18 @@ def test_fused_plans_match_torch_modules(net, board):
     for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 3e-2)):
         plan = plan_cls(model, eng, dtype=dtype)
         eng.planes.copy_(x32.to(dtype))
+        eng.leaf_states.copy_(st)
         plan(eng)
         torch.cuda.synchronize()
         assert torch.isfinite(eng.priors).all()
         assert (eng.priors.sum(1) - 1).abs().max() < 1e-3
         assert (eng.priors - p_ref).abs().max().item() < tol, (net, board, dtype, (eng.priors - p_ref).abs().max().item())
         assert (eng.values - v_ref).abs().max().item() < tol * (1 if dtype == torch.float32 else 3)
+        if dtype != torch.float32:  # the library-conv0 variant of the same plan must agree as well
+            plan2 = plan_cls(model, eng, dtype=dtype, use_stem=False)
+            eng.planes.copy_(x32.to(dtype))
+            plan2(eng)
+            assert (eng.priors - p_ref).abs().max().item() < tol
         # the un-fused evaluator (plain module on the same planes) must agree too
         ev = DeviceEvaluator(model, eng, dtype=dtype, channels_last=True)
         eng.planes.copy_(x32.to(dtype))
