@@ -213,6 +213,85 @@ class BatchedSelfPlay:
             self.played_games.append((games_idxs[g], moves_played[g], [r["visits"] for r in hist[g]], z))
         return self.played_games
 
+    def play_games_device(self, games_idxs, seed=0, start_states=None, with_features=True):
+        """Throughput mode: the whole game loop stays on the device -- Dirichlet noise pre-drawn for every move
+        (the reference draws it over ALL A entries and only then multiplies by the legal mask, mcts.py:220-223, so it
+        does not depend on the position), temperature sampling with torch.multinomial, re-rooting with the sampled
+        moves, samples accumulated in HBM -- and nothing synchronises with the host between moves.  Same algorithm
+        and hyper-parameters as play_games(); the random streams differ (one device generator instead of one legacy
+        NumPy stream per game), so games are not seed-identical to the reference's."""
+        eng, sp = self.eng, self.params.self_play
+        n, A, dev = eng.n_games, eng.A, eng.device
+        games_idxs = list(games_idxs)
+        assert len(games_idxs) == n, "play_games_device fills every engine slot"
+        alpha, coeff = sp.noise
+        num_read = sp.mcts.mcts_num_read
+        temp_sched = sp.mcts.temperature
+        n_edges = eng.L * (eng.C + 1) + eng.C * (eng.L + 1)
+        eng.set_cpuct(sp.mcts.mcts_cpuct)
+        eng.reset_roots(start_states)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(seed))
+        roots0 = eng.root_states()
+        played0 = int((~eng.valid_moves(roots0[:1])).sum().item()) - (A - n_edges)  # plies already on the board
+        n_moves = n_edges - played0
+        noise_all = None
+        if alpha > 0:
+            g = torch._standard_gamma(torch.full((n_moves, n, A), float(alpha), dtype=torch.float64, device=dev), generator=gen)
+            noise_all = g / g.sum(-1, keepdim=True)
+        temperature = None
+        hist_states, hist_visits, hist_active, hist_moves, hist_stats, hist_q = [], [], [], [], [], []
+        for move_i in range(n_moves):
+            if move_i in temp_sched:
+                temperature = float(temp_sched[move_i])
+            roots = eng.root_states()
+            valid = eng.valid_moves(roots)
+            active = eng.result(roots) == RESULT_NONE
+            k = n_moves - move_i  # legal moves left: one edge is played per move
+            reads = torch.where(active, torch.full((n,), _n_searches(k, num_read), dtype=torch.int32, device=dev),
+                                torch.full((n,), -1, dtype=torch.int32, device=dev))
+            noise = noise_all[move_i] * valid if noise_all is not None else None
+            eng.run_search(reads, self.ev, noise=noise, coeff=coeff, max_reads=_n_searches(k, num_read), graph_waves=self.graph_waves)
+            vis = eng.root_visits()
+            stats, _rw, q = eng.tree_stats()
+            v = vis.double()
+            probs = (v / v.max(1, keepdim=True).values.clamp_min(1.0)) ** (1.0 / temperature)
+            probs = torch.where(active.unsqueeze(1), probs, valid.double())  # finished games: any legal filler, ignored below
+            probs = probs + (probs.sum(1, keepdim=True) == 0).double()       # ... or a dummy row if the board is full
+            moves = torch.multinomial(probs, 1, generator=gen).reshape(-1).int()
+            moves = torch.where(active, moves, torch.full_like(moves, -1))
+            hist_states.append(roots); hist_visits.append(vis); hist_active.append(active); hist_moves.append(moves)
+            hist_stats.append(stats); hist_q.append(q)
+            eng.advance_roots(moves, reuse=bool(sp.reuse_mcts_tree))
+        final = eng.root_states()
+        res = eng.result(final)
+        info = eng.status()  # the only host synchronisation of the whole batch of games
+        self.total_sims = info["sims"]
+        self._device_hist = dict(states=hist_states, visits=hist_visits, active=hist_active, moves=hist_moves, stats=hist_stats,
+                                 q=hist_q, final=final, result=res, games_idxs=games_idxs, with_features=with_features)
+        return info
+
+    def device_samples(self):
+        """(planes int16 [R, 3, L+1, C+1], pi float64 [R, A], z float32 [R], game slot [R], move index [R]) of the last
+        play_games_device() call, still on the device (rows of finished games are dropped)."""
+        h, eng = self._device_hist, self.eng
+        final_np_tp = None
+        winner = (h["final"].view(torch.uint8).reshape(eng.n_games, 32)[:, 21]).to(torch.int8)  # just_played of the terminal state
+        z_final = h["result"].float()
+        planes, pis, zs, slots, mis = [], [], [], [], []
+        for mi, (st, vis, act) in enumerate(zip(h["states"], h["visits"], h["active"])):
+            idx = torch.nonzero(act).reshape(-1)
+            if idx.numel() == 0:
+                continue
+            to_play = st.view(torch.uint8).reshape(eng.n_games, 32)[:, 20].to(torch.int8)
+            planes.append(eng.features(st, torch.int16)[idx])
+            v = vis[idx].double()
+            pis.append(v / v.sum(1, keepdim=True).clamp_min(1.0))
+            zs.append(torch.where(to_play[idx] == winner[idx], z_final[idx], -z_final[idx]))
+            slots.append(idx)
+            mis.append(torch.full_like(idx, mi))
+        return torch.cat(planes), torch.cat(pis), torch.cat(zs), torch.cat(slots), torch.cat(mis)
+
     def get_games_moves(self):
         moves, vcs = [], []
         for _, mv, vis, _ in self.played_games:

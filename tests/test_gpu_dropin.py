@@ -161,3 +161,42 @@ def test_batched_selfplay_matches_reference_games(api):
         assert list(df.columns) == games[0]["columns"]
         assert np.array_equal(df.to_numpy(dtype=np.float64), ref_rows)
     eng.close()
+
+
+def test_device_resident_selfplay_is_valid_play(api):
+    """play_games_device(): no host sync between moves, device RNG.  Not seed-identical to the reference, so
+    check what is invariant: every recorded move is legal, games end exactly when the oracle says they do, the
+    result and z signs agree with the oracle, visit totals equal the simulation budget plus the reused subtree."""
+    from oracle import oracle
+    eng = api["engine"].Engine((3, 3), n_games=48, max_nodes=2048)
+    G = SELFPLAY[0]
+    bsp = api["self_play"].BatchedSelfPlay(eng, api["engine"].FakeNetEvaluator(0), _params(api, G), graph_waves=8)
+    info = bsp.play_games_device(range(48), seed=5)
+    assert info["errors"] == 0
+    h = bsp._device_hist
+    moves = torch.stack(h["moves"]).cpu().numpy()       # [n_moves, n]
+    active = torch.stack(h["active"]).cpu().numpy()
+    visits = torch.stack(h["visits"]).cpu().numpy()
+    res = h["result"].cpu().numpy()
+    planes, pi, z, slot, mi = (x.cpu().numpy() for x in bsp.device_samples())
+    assert np.allclose(pi.sum(1), 1.0) and set(np.unique(z)).issubset({-1.0, 0.0, 1.0})
+    assert planes.shape[0] == active.sum()
+    for g in range(48):
+        og = oracle.OracleGame(3, 3)
+        carried = 0
+        for m in range(moves.shape[0]):
+            if og.result() is not None:
+                assert not active[m, g] and moves[m, g] == -1
+                continue
+            assert active[m, g]
+            k = int(og.valid_moves().sum())
+            import math
+            n_reads = min(4 * math.factorial(k), G["num_read"])
+            assert visits[m, g].sum() == n_reads + carried
+            assert og.valid_moves()[moves[m, g]]
+            rows = np.flatnonzero((slot == g) & (mi == m))
+            assert len(rows) == 1 and np.array_equal(planes[rows[0]].ravel(), og.features().ravel())
+            carried = max(int(visits[m, g][moves[m, g]]) - 1, 0) if visits[m, g][moves[m, g]] > 0 else 0
+            og.play_(int(moves[m, g]))
+        assert og.result() == int(res[g])
+    eng.close()

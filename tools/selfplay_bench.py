@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Full self-play games (not single searches): games/hour and sims/s, BASELINE configs[1] and configs[3].
+    python tools/selfplay_bench.py --board 3x3 --games 4096 --net simple
+    python tools/selfplay_bench.py --board 5x5 --games 16384 --net resnet --max-nodes 4096
+Prints one JSON line per run."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--board", default="3x3")
+    ap.add_argument("--games", type=int, default=4096)
+    ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--net", default="simple", choices=["simple", "resnet", "fake"])
+    ap.add_argument("--max-nodes", type=int, default=8192)
+    ap.add_argument("--mode", default="device", choices=["device", "host"])
+    ap.add_argument("--repeats", type=int, default=1)
+    args = ap.parse_args()
+    import torch
+    from dotsboxesaz_b200 import engine, self_play
+    from dotsboxesaz_b200.nn import FusedResNetZero, FusedSimpleNN, ResNetZero, resnet_zero_parameters
+    from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
+    from dotsboxesaz_b200.utils.utils import DotDict
+    L, C = (int(x) for x in args.board.split("x"))
+    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.max_nodes)
+    torch.manual_seed(0)
+    if args.net == "fake":
+        ev = engine.FakeNetEvaluator(0)
+    elif args.net == "simple":
+        ev = FusedSimpleNN(SimpleNN(board=(L, C)), eng)
+    else:
+        ev = FusedResNetZero(ResNetZero(DotDict({"nn": {"model_parameters": resnet_zero_parameters((L, C))}})), eng)
+    params = DotDict({"self_play": {"reuse_mcts_tree": True, "noise": (0.8, 0.25),
+                                    "mcts": {"mcts_num_read": args.sims, "mcts_cpuct": (1.25, 19652),
+                                             "temperature": {0: 1.0, 12: 0.02}, "max_async_searches": 1}}})
+    for rep in range(args.repeats + 1):  # first pass warms up (graphs, cuDNN)
+        sp = self_play.BatchedSelfPlay(eng, ev, params, graph_waves=16)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        if args.mode == "device":
+            info = sp.play_games_device(range(args.games), seed=rep)
+            rows = sp.device_samples()[0].shape[0]
+        else:
+            sp.play_games(range(args.games), seeds=range(rep * args.games, (rep + 1) * args.games))
+            info = {"sims": sp.total_sims, "max_nodes_used": None, "path_nodes": 0, "terminal_leaves": 0}
+            rows = len(sp.rows)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        if rep == 0:
+            continue
+        print(json.dumps({"board": args.board, "games": args.games, "sims_per_move": args.sims, "net": args.net, "mode": args.mode,
+                          "seconds": dt, "games_per_hour": args.games / dt * 3600, "sims_per_sec": info["sims"] / dt,
+                          "total_sims": info["sims"], "sample_rows": rows, "max_nodes_used": info["max_nodes_used"],
+                          "mean_path_nodes": info["path_nodes"] / max(1, info["sims"]),
+                          "terminal_leaf_frac": info["terminal_leaves"] / max(1, info["sims"])}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
