@@ -144,8 +144,21 @@ class AlphaZeroLoss(nn.Module):
         return loss_v + loss_pi, (loss_pi.item(), loss_v.item())
 
 
+class _NullWriter:
+    def add_scalar(self, *a, **k):
+        pass
+
+    def add_scalars(self, *a, **k):
+        pass
+
+    def add_text(self, *a, **k):
+        pass
+
+
 class NeuralNetWrapper:
-    """nn.py:145-173: the host-facing predict API (numpy in, numpy out).  Training lives in train.py."""
+    """nn.py:145-274: host-facing predict API (numpy in, numpy out) and the supervised training step of a
+    generation (SGD, AlphaZeroLoss, one random board symmetry per batch, checkpoint per generation).  Plain
+    PyTorch: training is not on the self-play hot path."""
 
     def __init__(self, model, params):
         self.params = params
@@ -170,6 +183,66 @@ class NeuralNetWrapper:
 
     async def __call__(self, X):
         return await self.predict(X)
+
+    def train(self, train_dataset, val_dataset, writer, generation):
+        """nn.py:175-274.  Returns the running batch index (stored in the checkpoint)."""
+        import torch.utils.data as data
+        writer = writer or _NullWriter()
+        tp = self.params.nn.train_params
+        train_data = data.DataLoader(train_dataset, tp.train_batch_size, shuffle=True, drop_last=True)
+        val_data = data.DataLoader(val_dataset, tp.val_batch_size, shuffle=False, drop_last=True) if val_dataset is not None else None
+        criterion = AlphaZeroLoss()
+        optimizer = torch.optim.SGD(self.model.parameters(), lr=tp.lr, **tp.optimizer_params)
+        batch_i = 0
+        if generation > 0:
+            batch_i = load_checkpoint(self.params.nn.chkpts_filename.format(generation - 1), self.model, optimizer, self.device)
+        writer.add_scalar("lr", tp.lr, batch_i)
+
+        def accuracy(v, z, threshold=0.5):
+            ok = z.sign().eq(v.sign()) & (v - z).abs().lt(threshold)
+            return ok.sum().item(), z.size(0)
+
+        for epoch in range(min(2 * generation, tp.nb_epochs)):
+            self.model.train(True)
+            tr_loss, tr_batches, tr_ok, tr_tot = 0.0, 0, 0, 1
+            for boards, pi, z in train_data:
+                batch_i += 1
+                tr_batches += 1
+                boards, pi, z = boards.to(self.device), pi.to(self.device), z.to(self.device)
+                boards, pi = tp.symmetries(boards, pi)
+                p, v = self.model(boards)
+                loss, (loss_pi, loss_v) = criterion(p, v, pi, z)
+                loss.backward()
+                optimizer.step()
+                optimizer.zero_grad()
+                with torch.no_grad():
+                    c, t = accuracy(v, z)
+                tr_ok += c; tr_tot += t
+                tr_loss += loss_pi + loss_v
+                writer.add_scalars("loss", {"pi/train": loss_pi, "v/train": loss_v, "total/train": loss_pi + loss_v}, batch_i)
+            val_loss, va_ok, va_tot = 0.0, 0, 1
+            if val_data is not None:
+                self.model.train(False)
+                lv = lp = 0.0
+                nb = 0
+                with torch.no_grad():
+                    for boards, pi, z in val_data:
+                        nb += 1
+                        boards, pi, z = boards.to(self.device), pi.to(self.device), z.to(self.device)
+                        boards, pi = tp.symmetries(boards, pi)
+                        p, v = self.model(boards)
+                        c, t = accuracy(v, z)
+                        va_ok += c; va_tot += t
+                        _, (a, b) = criterion(p, v, pi, z)
+                        lp += a; lv += b
+                if nb:
+                    val_loss = (lp + lv) / nb
+                    writer.add_scalars("loss", {"pi/eval": lp / nb, "v/eval": lv / nb, "total/eval": val_loss}, batch_i)
+            writer.add_scalars("accuracy", {"v/train": tr_ok / tr_tot, "v/eval": va_ok / va_tot}, batch_i)
+            writer.add_scalar("generation", generation, batch_i)
+            print(f"Epoch {epoch}, train loss= {tr_loss / max(tr_batches, 1):5f}, validation loss= {val_loss:5f}", flush=True)
+        save_checkpoint(self.params.nn.chkpts_filename.format(generation), self.model, optimizer, batch_i)
+        return batch_i
 
 
 class GenerationLrScheduler:
@@ -398,3 +471,17 @@ class FusedResNetZero:
         self.logits[:, :self.A] = out[:, :self.A]
         self.logits[:, self.A:self.A + 1] = torch.addmm(self.v_b, F.relu(out[:, self.A:]), self.v_w)
         eng.nn_heads(self.logits)
+
+
+def make_evaluator(model, engine, dtype=torch.bfloat16):
+    """The fastest evaluator available for `model`: a fused inference plan for the two reference architectures,
+    the plain module otherwise.  Plans snapshot (fold) the weights: build a new one after every training step."""
+    from .dots_boxes.dots_boxes_nn import SimpleNN
+    try:
+        if isinstance(model, SimpleNN):
+            return FusedSimpleNN(model, engine, dtype=dtype)
+        if isinstance(model, ResNetZero):
+            return FusedResNetZero(model, engine, dtype=dtype)
+    except NotImplementedError:
+        pass
+    return DeviceEvaluator(model, engine, dtype=dtype)

@@ -300,7 +300,38 @@ class BatchedSelfPlay:
         return moves, np.asarray(vcs, dtype=float)
 
     def get_datasets(self, generation, with_features=True):
+        if not self.rows and getattr(self, "_device_hist", None) is not None:
+            self._rows_from_device(with_features)
         return _dataset(self.rows, generation, with_features)
+
+    def _rows_from_device(self, with_features=True):
+        """Turn the device-resident history of play_games_device() into the row dicts of get_datasets()."""
+        h, eng = self._device_hist, self.eng
+        n = eng.n_games
+        res = h["result"].cpu().numpy()
+        winner = eng.states_to_numpy(h["final"])["just_played"]
+        act = torch.stack(h["active"]).cpu().numpy()
+        moves = torch.stack(h["moves"]).cpu().numpy()
+        vis = torch.stack(h["visits"]).cpu().numpy()
+        stats = torch.stack(h["stats"]).cpu().numpy()
+        q = torch.stack(h["q"]).cpu().numpy()
+        to_play = np.stack([eng.states_to_numpy(s)["to_play"] for s in h["states"]])
+        feats = None
+        if with_features:
+            feats = torch.stack([eng.features(s, torch.int16) for s in h["states"]]).cpu().numpy().reshape(len(h["states"]), n, -1)
+        for g in range(n):
+            z = int(res[g])
+            for m in range(act.shape[0]):
+                if not act[m, g]:
+                    continue
+                v = vis[m, g]
+                self.rows.append({"game_idx": h["games_idxs"][g], "move_idx": m, "move": int(moves[m - 1, g]) if m else None,
+                                  "player": int(to_play[m, g]), "visits": v, "pi": v / (v.sum() or 1.0),
+                                  "z": z if to_play[m, g] == winner[g] else -z,
+                                  "stats": (int(stats[m, g][1]), int(stats[m, g][2]), int(stats[m, g][3]), np.float32(q[m, g])),
+                                  "features": feats[m, g] if with_features else None})
+            self.played_games.append((h["games_idxs"][g], [int(x) for x in moves[:, g] if x >= 0],
+                                      [vis[m, g] for m in range(act.shape[0]) if act[m, g]], z))
 
 
 def shard_game_indices(n_games, rank, world):
@@ -347,7 +378,7 @@ def generate_games(hdf_file_name, generation, nn_class, n_games, params, n_worke
     to `writer(hdf_file_name, "fresh", df)` (default: pandas HDFStore append, as utils/utils.py:94-96)."""
     import torch.distributed as dist
     from . import engine as _engine
-    from .nn import DeviceEvaluator
+    from .nn import make_evaluator
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     mine = shard_game_indices(n_games, rank, world)
@@ -360,12 +391,17 @@ def generate_games(hdf_file_name, generation, nn_class, n_games, params, n_worke
         if generation != 0:
             model.load_parameters(generation - 1, to_device=engine.device)
         broadcast_model(model.to(engine.device))
-        evaluator = DeviceEvaluator(model, engine)
+        evaluator = make_evaluator(model, engine)
     frames = []
+    base_seed = int(params.self_play.get("seed", 0) or 0)
+    host_rng = params.self_play.get("rng", "device") == "host"  # "host": one legacy NumPy stream per game (reference-exact games)
     for lo in range(0, len(mine), engine.n_games):
         chunk = mine[lo:lo + engine.n_games]
         sp = BatchedSelfPlay(engine, evaluator, params)
-        sp.play_games(chunk, seeds=[int(params.self_play.get("seed", 0) or 0) + i for i in chunk])
+        if host_rng or len(chunk) < engine.n_games:
+            sp.play_games(chunk, seeds=[base_seed + i for i in chunk])
+        else:
+            sp.play_games_device(chunk, seed=base_seed + 7919 * generation + chunk[0])
         frames.append(sp.get_datasets(generation, True))
     df = pd.concat(frames) if frames else None
     df = gather_samples(df)

@@ -275,6 +275,36 @@ def gen_selfplay():
     return out
 
 
+# -------------------------------------------------------------- symmetries
+def gen_symmetries():
+    """Outputs of the reference's SymmetriesGenerator (dots_boxes_nn.py:11-58) for each of its 8 choices."""
+    import importlib
+    import torch
+    ref_nn = importlib.import_module("dots_boxes.dots_boxes_nn")
+    gen = ref_nn.SymmetriesGenerator()
+    out = []
+    for L in (3, 5):
+        r = L + 1
+        torch.manual_seed(L)
+        b = torch.randint(0, 2, (5, 3, r, r)).float()
+        b[:, 0, :, -1] = 0; b[:, 1, -1, :] = 0
+        b[:, 2] = torch.randint(1, 9, (5, 1, 1)).float()
+        p = torch.rand(5, 2, r, r)
+        p[:, 0, :, -1] = 0; p[:, 1, -1, :] = 0   # policies carry no mass on padding slots
+        p = p.reshape(5, -1)
+        rec = {"L": L, "boards": hx(b.numpy(), np.float32), "policies": hx(p.numpy(), np.float32), "out": []}
+        for i in range(8):
+            orig = random.randint
+            random.randint = lambda a, b_, i=i: i
+            try:
+                rb, rp = gen(b.clone(), p.clone())
+            finally:
+                random.randint = orig
+            rec["out"].append({"boards": hx(rb.numpy(), np.float32), "policies": hx(rp.reshape(5, -1).numpy(), np.float32)})
+        out.append(rec)
+    return out
+
+
 def dump(name, obj):
     import gzip
     with gzip.GzipFile(os.path.join(OUT, name + ".json.gz"), "wb", mtime=0) as fh:
@@ -282,13 +312,15 @@ def dump(name, obj):
 
 
 def main():
-    which = sys.argv[1:] or ["games", "mcts", "selfplay"]
+    which = sys.argv[1:] or ["games", "mcts", "selfplay", "symmetries"]
     if "games" in which:
         dump("games", gen_games())
     if "mcts" in which:
         dump("mcts", gen_mcts())
     if "selfplay" in which:
         dump("selfplay", gen_selfplay())
+    if "symmetries" in which:
+        dump("symmetries", gen_symmetries())
 
 
 if __name__ == "__main__":
