@@ -315,12 +315,11 @@ static int best_child(const orc_tree *t, const orc_node *n, double cpuct, double
     return best;
 }
 
-/* One _search() (mcts.py:184-199) with select_leaf (105-114), expand (116-119)
- * and backup (121-132) inlined; strictly sequential (max_pending_evals == 1). */
-static void one_search(orc_tree *t, orc_nn_fn nn, void *user, double cpuct, double cpuct_base)
+/* select_leaf (mcts.py:105-114): the first half of one _search(), up to the point where the
+ * reference awaits the net.  Virtual loss is subtracted from every node left behind. */
+static int select_path(orc_tree *t, double cpuct, double cpuct_base, orc_node **path)
 {
     const orc_game *g = &t->g;
-    orc_node *path[ORC_MAX_A + 2];
     int np_ = 0;
     orc_node *cur = t->first;
     path[np_++] = cur;
@@ -337,7 +336,14 @@ static void one_search(orc_tree *t, orc_nn_fn nn, void *user, double cpuct, doub
         cur = cur->children[best];
         path[np_++] = cur;
     }
-    orc_node *leaf = cur;
+    return np_;
+}
+
+/* the second half of _search() (mcts.py:186-199): evaluate the leaf, mask/renormalise, expand, backup */
+static void finish_path(orc_tree *t, orc_nn_fn nn, void *user, orc_node **path, int np_)
+{
+    const orc_game *g = &t->g;
+    orc_node *leaf = path[np_ - 1];
     float value;
     if (!leaf->is_terminal) {
         float p[ORC_MAX_A];
@@ -369,12 +375,29 @@ static void one_search(orc_tree *t, orc_nn_fn nn, void *user, double cpuct, doub
     t->sims_done += 1; t->path_nodes += np_;
 }
 
-/* UCT_search (mcts.py:183-244) for max_pending_evals == 1.
+/* One _search() (mcts.py:184-199), strictly sequential (max_pending_evals == 1). */
+static void one_search(orc_tree *t, orc_nn_fn nn, void *user, double cpuct, double cpuct_base)
+{
+    orc_node *path[ORC_MAX_A + 2];
+    int np_ = select_path(t, cpuct, cpuct_base, path);
+    finish_path(t, nn, user, path, np_);
+}
+
+/* UCT_search (mcts.py:183-244); max_pending == 1 is the strictly sequential case.
  * noise == NULL <=> alpha <= 0 (then noise is the scalar 0.0 in the reference).
  * noise (float64[A]) is the host-drawn Dirichlet sample already multiplied by
  * the legal mask (mcts.py:220-223). */
+int orc_uct_search_k(orc_tree *t, int num_reads, orc_nn_fn nn, void *user,
+                     double cpuct, double cpuct_base, const double *noise, double coeff, int max_pending);
+
 int orc_uct_search(orc_tree *t, int num_reads, orc_nn_fn nn, void *user,
                    double cpuct, double cpuct_base, const double *noise, double coeff)
+{
+    return orc_uct_search_k(t, num_reads, nn, user, cpuct, cpuct_base, noise, coeff, 1);
+}
+
+int orc_uct_search_k(orc_tree *t, int num_reads, orc_nn_fn nn, void *user,
+                     double cpuct, double cpuct_base, const double *noise, double coeff, int max_pending)
 {
     const int A = t->g.A;
     orc_node *root = t->first;
@@ -409,7 +432,32 @@ int orc_uct_search(orc_tree *t, int num_reads, orc_nn_fn nn, void *user,
         root->priors_f64 = 0;
     }
 
-    for (int i = 0; i < num_reads; ++i) one_search(t, nn, user, cpuct, cpuct_base);
+    if (max_pending <= 1) {
+        for (int i = 0; i < num_reads; ++i) one_search(t, nn, user, cpuct, cpuct_base);
+        return 0;
+    }
+    /* mcts.py:228-242 with a net that suspends each _search() exactly once: the event loop then runs the
+     * simulations in waves -- `max_pend` select_leaf()s back to back (each leaving its virtual loss behind; a terminal
+     * leaf is expanded and backed up at once because it never awaits), then the evaluations / expands / backups of the
+     * others in the same order -- the first wave min(max_pending_evals, A) wide, later ones max_pending_evals wide,
+     * the last one whatever is left. */
+    {
+        static orc_node *paths[ORC_MAX_A][ORC_MAX_A + 2];
+        int lens[ORC_MAX_A];
+        int cap = max_pending < A ? max_pending : A, done = 0;
+        if (cap > ORC_MAX_A) cap = ORC_MAX_A;
+        while (done < num_reads) {
+            int w = num_reads - done < cap ? num_reads - done : cap;
+            for (int k = 0; k < w; ++k) {
+                lens[k] = select_path(t, cpuct, cpuct_base, paths[k]);
+                /* a terminal leaf never awaits the net (mcts.py:186,194-196): its _search() runs to completion on the spot */
+                if (paths[k][lens[k] - 1]->is_terminal) { finish_path(t, nn, user, paths[k], lens[k]); lens[k] = 0; }
+            }
+            for (int k = 0; k < w; ++k) if (lens[k]) finish_path(t, nn, user, paths[k], lens[k]);
+            done += w;
+            cap = max_pending > ORC_MAX_A ? ORC_MAX_A : max_pending;
+        }
+    }
     return 0;
 }
 

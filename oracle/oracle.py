@@ -56,6 +56,8 @@ def lib():
         L.orc_tree_free.argtypes = [C.c_void_p]
         L.orc_uct_search.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                      C.c_void_p, C.c_double]
+        L.orc_uct_search_k.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                       C.c_void_p, C.c_double, C.c_int]
         L.orc_reroot.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_root_arrays.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.orc_root_state.argtypes = [C.c_void_p, C.POINTER(State)]
@@ -164,15 +166,15 @@ class OracleTree:
             lib().orc_tree_free(self.t)
             self.t = None
 
-    def search(self, num_reads, cpuct=(1.25, 19652), noise=None, coeff=0.0):
+    def search(self, num_reads, cpuct=(1.25, 19652), noise=None, coeff=0.0, max_pending=1):
         fn = C.cast(self._cb, C.c_void_p) if self._cb is not None else C.cast(lib().orc_fake_nn, C.c_void_p)
         user = None if self._cb is not None else C.cast(C.byref(self._kind), C.c_void_p)
         nz = None
         if noise is not None:
             nz = np.ascontiguousarray(noise, dtype=np.float64)
             assert nz.shape == (self.A,)
-        lib().orc_uct_search(self.t, int(num_reads), fn, user, float(cpuct[0]), float(cpuct[1]),
-                             None if nz is None else nz.ctypes.data_as(C.c_void_p), float(coeff))
+        lib().orc_uct_search_k(self.t, int(num_reads), fn, user, float(cpuct[0]), float(cpuct[1]),
+                               None if nz is None else nz.ctypes.data_as(C.c_void_p), float(coeff), int(max_pending))
         return self.root()["visits"]
 
     def reroot(self, move, reuse=True):

@@ -52,8 +52,12 @@ def fake_nn_eval(state, kind):
     return p, v
 
 
-def make_nn(kind):
+def make_nn(kind, yielding=False):
+    """yielding: suspend once, like a real batched net would; with max_pending_evals = K the reference's event loop
+    then runs the simulations in deterministic waves of K select_leaf()s followed by their K backups."""
     async def nn(state):
+        if yielding:
+            await asyncio.sleep(0)
         return fake_nn_eval(state, kind)
     return nn
 
@@ -159,14 +163,14 @@ class NoiseTap:
         np.random.dirichlet = self._orig
 
 
-def run_session(L, C, pre_moves, script, kind, seed=None):
+def run_session(L, C, pre_moves, script, kind, seed=None, max_pending=1):
     """script: list of ("search", num_reads, (alpha, coeff)) | ("reroot", move|"argmax", reuse)."""
     set_board(L, C)
     s = BoxesState()
     for m in pre_moves:
         s.play_(int(m))
     root = mcts.create_root_uct_node(s)
-    nn = make_nn(kind)
+    nn = make_nn(kind, yielding=max_pending > 1)
     if seed is not None:
         np.random.seed(seed)
     steps = []
@@ -177,7 +181,7 @@ def run_session(L, C, pre_moves, script, kind, seed=None):
             if op[0] == "search":
                 _, n, dirichlet = op
                 tap.last = None
-                asyncio.run(mcts.UCT_search(root, n, nn, cpuct=CPUCT, max_pending_evals=1, dirichlet=dirichlet))
+                asyncio.run(mcts.UCT_search(root, n, nn, cpuct=CPUCT, max_pending_evals=max_pending, dirichlet=dirichlet))
                 rec = {"op": "search", "num_reads": n, "alpha": dirichlet[0], "coeff": dirichlet[1]}
                 if tap.last is not None:
                     rec["noise"] = hx(tap.last * root.game_state.get_valid_moves(), np.float64)
@@ -190,7 +194,7 @@ def run_session(L, C, pre_moves, script, kind, seed=None):
                 root = mcts.init_mcts_tree(root, int(mv), reuse_tree=reuse)
                 steps.append({"op": "reroot", "move": int(mv), "reuse": bool(reuse), "root": root_record(root)})
     return {"L": L, "C": C, "pre_moves": [int(m) for m in pre_moves], "kind": kind, "seed": seed,
-            "cpuct": list(CPUCT), "steps": steps}
+            "cpuct": list(CPUCT), "steps": steps, "max_pending": max_pending}
 
 
 def full_game_script(n, dirichlet=(0.0, 0.0), max_moves=80, reuse=True):
@@ -305,6 +309,25 @@ def gen_symmetries():
     return out
 
 
+def gen_mcts_pending():
+    """max_pending_evals > 1 (the reference ships 64, configuration.py:35) with a net that yields once per call."""
+    out = []
+    out.append(run_session(3, 3, [], full_game_script(800), 0, max_pending=8))
+    out.append(run_session(3, 3, [6, 20], full_game_script(800), 0, max_pending=64))
+    out.append(run_session(3, 3, [], full_game_script(203, (0.8, 0.25)), 1, seed=3, max_pending=5))
+    out.append(run_session(5, 5, [], full_game_script(400, max_moves=12), 0, max_pending=64))
+    out.append(run_session(5, 5, [3], full_game_script(150, (0.8, 0.25)), 0, seed=4, max_pending=16))
+    out.append(run_session(2, 2, [], full_game_script(100), 1, max_pending=64))
+    out.append(run_session(3, 3, [], [("search", 5, (0.0, 0.0)), ("reroot", 27, True), ("search", 40, (0.0, 0.0)),
+                                      ("search", 7, (0.0, 0.0)), ("reroot", "argmax", False), ("search", 33, (0.0, 0.0))], 0,
+                           max_pending=4))
+    for i, moves, _nxt, _z in load_csv_positions()[::4]:
+        s = run_session(3, 3, moves, [("search", 300, (0.0, 0.0))], i % 2, max_pending=8 if i % 3 else 64)
+        s["csv_id"] = i
+        out.append(s)
+    return out
+
+
 def dump(name, obj):
     import gzip
     with gzip.GzipFile(os.path.join(OUT, name + ".json.gz"), "wb", mtime=0) as fh:
@@ -312,7 +335,7 @@ def dump(name, obj):
 
 
 def main():
-    which = sys.argv[1:] or ["games", "mcts", "selfplay", "symmetries"]
+    which = sys.argv[1:] or ["games", "mcts", "selfplay", "symmetries", "mcts_pending"]
     if "games" in which:
         dump("games", gen_games())
     if "mcts" in which:
@@ -321,6 +344,8 @@ def main():
         dump("selfplay", gen_selfplay())
     if "symmetries" in which:
         dump("symmetries", gen_symmetries())
+    if "mcts_pending" in which:
+        dump("mcts_pending", gen_mcts_pending())
 
 
 if __name__ == "__main__":

@@ -8,6 +8,7 @@ from oracle import oracle
 
 GAMES = load("games")
 MCTS = load("mcts")
+MCTS_PENDING = load("mcts_pending")
 SELFPLAY = load("selfplay")
 
 
@@ -57,9 +58,9 @@ def _check_root(r, ref, where):
     _cmp_state(r["state"].record(), ref["state"], where, full_hash=False)
 
 
-@pytest.mark.parametrize("si", range(len(MCTS)))
+@pytest.mark.parametrize("si", range(len(MCTS) + len(MCTS_PENDING)))
 def test_mcts_sessions(si):
-    S = MCTS[si]
+    S = MCTS[si] if si < len(MCTS) else MCTS_PENDING[si - len(MCTS)]
     start = oracle.OracleGame(S["L"], S["C"])
     for m in S["pre_moves"]:
         start.play_(m)
@@ -68,7 +69,7 @@ def test_mcts_sessions(si):
     for i, st in enumerate(S["steps"]):
         if st["op"] == "search":
             noise = unhex(st["noise"], np.float64) if "noise" in st else None
-            t.search(st["num_reads"], cpuct=S["cpuct"], noise=noise, coeff=st["coeff"])
+            t.search(st["num_reads"], cpuct=S["cpuct"], noise=noise, coeff=st["coeff"], max_pending=S.get("max_pending", 1))
         else:
             t.reroot(st["move"], st["reuse"])
         _check_root(t.root(S["cpuct"]), st["root"], (si, i, st["op"]))
