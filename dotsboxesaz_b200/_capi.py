@@ -20,7 +20,7 @@ assert STATE_DTYPE.itemsize == 32
 
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("board_l", C.c_int32), ("board_c", C.c_int32),
-                ("n_games", C.c_int32), ("max_nodes", C.c_int32), ("lut_size", C.c_int32), ("reserved", C.c_int32),
+                ("n_games", C.c_int32), ("max_nodes", C.c_int32), ("lut_size", C.c_int32), ("max_pending", C.c_int32),
                 ("cpuct", C.c_double), ("cpuct_base", C.c_double)]
 
 
@@ -41,7 +41,7 @@ SYMBOLS = {
     "dbaz_game_features": (C.c_int, [_P, _P, _P, _I32, _I32, _I64, _U64]),
     "dbaz_game_random_rollout": (C.c_int, [_P, _P, _U64, _U64, _P, _P, _I32, _I64, _U64]),
     "dbaz_search_reset_roots": (C.c_int, [_P, _P, _U64]),
-    "dbaz_search_begin": (C.c_int, [_P, _P, _P, _D, _U64]),
+    "dbaz_search_begin": (C.c_int, [_P, _P, _I32, _P, _D, _U64]),
     "dbaz_search_step": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _U64]),
     "dbaz_search_stop": (C.c_int, [_P, _U64]),
     "dbaz_search_root_visits": (C.c_int, [_P, _P, _U64]),

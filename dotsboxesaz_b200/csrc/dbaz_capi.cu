@@ -24,6 +24,7 @@ struct dbaz_engine {
     size_t adv_smem;
     const double* noise;  // caller-owned device buffer of the current search (may be null)
     double coeff;
+    int pending;          // max_pending_evals of the current search
     unsigned long long* d_status;
     std::string err;
 };
@@ -124,6 +125,8 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     if (L * C > 16000) return fail(nullptr, "board too large");
     if (cfg->n_games < 1) return fail(nullptr, "n_games must be >= 1");
     if (cfg->max_nodes < 2 || cfg->max_nodes > 65536) return fail(nullptr, "max_nodes must be in [2, 65536]");
+    const int max_pending = cfg->max_pending > 0 ? cfg->max_pending : 1;
+    if (max_pending > DBAZ_MAX_PENDING) return fail(nullptr, "max_pending too large");
     int ndev = 0;
     cudaError_t st = cudaGetDeviceCount(&ndev);
     if (st != cudaSuccess || ndev == 0)
@@ -152,6 +155,8 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     ta.n_trees = cfg->n_games;
     ta.max_nodes = cfg->max_nodes;
     ta.stride = 32 + 16 * A;
+    ta.max_pending = max_pending;
+    e->pending = 1;
     ta.lut_size = cfg->lut_size > 0 ? cfg->lut_size : 65536;
     ta.cpuct = cfg->cpuct;
     ta.cpuct_base = cfg->cpuct_base;
@@ -169,10 +174,10 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     bool ok = alloc((void**)&ta.arena, arena_bytes, "node pool") &&
               alloc((void**)&ta.trees, (size_t)ta.n_trees * sizeof(TreeRec), "tree table") &&
               alloc((void**)&ta.root_prior, (size_t)ta.n_trees * A * sizeof(double), "root priors") &&
-              alloc((void**)&ta.path, (size_t)ta.n_trees * PATH_CAP * sizeof(uint32_t), "paths") &&
+              alloc((void**)&ta.path, (size_t)max_pending * ta.n_trees * PATH_CAP * sizeof(uint32_t), "paths") &&
               alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double), "log table") &&
               alloc((void**)&ta.act_tab, (size_t)A * 2 * sizeof(uint4), "action table") &&
-              alloc((void**)&ta.leaf_hdr, (size_t)ta.n_trees * 2 * sizeof(uint4), "leaf headers") &&
+              alloc((void**)&ta.pend, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4), "pending leaves") &&
               alloc((void**)&e->d_status, 8 * sizeof(unsigned long long), "status");
     if (!ok) { dbaz_engine_destroy(e); return 1; }
     if (upload_lut(e)) { g_create_err = e->err; dbaz_engine_destroy(e); return 1; }
@@ -185,8 +190,8 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
         if (s1 != cudaSuccess || s2 != cudaSuccess) { g_create_err = "cannot reserve shared memory for re-rooting"; dbaz_engine_destroy(e); return 1; }
     }
     k_build_act_tab<<<1, DBAZ_MAX_ACTIONS>>>(b, const_cast<uint4*>(ta.act_tab));
-    cudaMemset(ta.leaf_hdr, 0, (size_t)ta.n_trees * 2 * sizeof(uint4));
-    cudaMemset(ta.path, 0, (size_t)ta.n_trees * PATH_CAP * sizeof(uint32_t));
+    cudaMemset(ta.pend, 0, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4));
+    cudaMemset(ta.path, 0, (size_t)max_pending * ta.n_trees * PATH_CAP * sizeof(uint32_t));
     // an all-empty-board root set so that the engine is usable right after create
     k_reset_roots<<<blocks_for(ta.n_trees, 128), 128>>>(b, ta, nullptr);
     if ((st = cudaDeviceSynchronize()) != cudaSuccess) { cuda_fail(nullptr, "k_reset_roots", st); dbaz_engine_destroy(e); return 1; }
@@ -203,7 +208,7 @@ void dbaz_engine_destroy(dbaz_engine* e) {
     cudaFree(e->ta.path);
     cudaFree(const_cast<double*>(e->ta.lut));
     cudaFree(const_cast<uint4*>(e->ta.act_tab));
-    cudaFree(e->ta.leaf_hdr);
+    cudaFree(e->ta.pend);
     cudaFree(e->d_status);
     delete e;
 }
@@ -211,7 +216,7 @@ void dbaz_engine_destroy(dbaz_engine* e) {
 int dbaz_engine_info(const dbaz_engine* e, int32_t* out8) {
     if (!e || !out8) return 1;
     out8[0] = e->board.L; out8[1] = e->board.C; out8[2] = e->board.A; out8[3] = e->board.F;
-    out8[4] = e->ta.n_trees; out8[5] = e->ta.max_nodes; out8[6] = e->ta.stride; out8[7] = e->n_sms;
+    out8[4] = e->ta.n_trees; out8[5] = e->ta.max_nodes; out8[6] = e->ta.stride; out8[7] = e->ta.max_pending;
     return 0;
 }
 
@@ -370,10 +375,12 @@ int dbaz_search_reset_roots(dbaz_engine* e, const dbaz_state* root_states, uint6
     return launch_ok(e, "k_reset_roots");
 }
 
-int dbaz_search_begin(dbaz_engine* e, const int32_t* num_reads, const double* noise, double coeff, uint64_t stream) {
+int dbaz_search_begin(dbaz_engine* e, const int32_t* num_reads, int32_t pending, const double* noise, double coeff,
+                      uint64_t stream) {
     if (!e || !num_reads) return 1;
+    if (pending < 1 || pending > e->ta.max_pending) return fail(e, "pending must be in [1, max_pending of the engine]");
     DeviceGuard guard(e->cfg.device);
-    e->noise = noise; e->coeff = coeff;
+    e->noise = noise; e->coeff = coeff; e->pending = pending;
     const int grid = blocks_for(e->ta.n_trees, TREE_WARPS);
     DBAZ_DISPATCH(e, (k_search_begin<APL, NW><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(e->board, e->ta, num_reads, noise, coeff)));
     return launch_ok(e, "k_search_begin");
@@ -386,7 +393,7 @@ int dbaz_search_step(dbaz_engine* e, const float* priors, const float* values, v
     DeviceGuard guard(e->cfg.device);
     const int grid = blocks_for(e->ta.n_trees, TREE_WARPS);
     DBAZ_DISPATCH(e, (k_search_step<APL, NW><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(
-                         e->board, e->ta, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, leaf_kind)));
+                         e->board, e->ta, e->pending, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, leaf_kind)));
     return launch_ok(e, "k_search_step");
 }
 

@@ -1,9 +1,12 @@
 // dbaz_tree_kernels.cuh -- the per-simulation hot path: PUCT select, lazy child creation,
 // feature gather, expand, backup, root-prior mix, re-root with in-place subtree compaction.
 //
-// One warp owns one tree (one game) and runs its simulations strictly in order, so no
-// atomics are needed and visit counts are bit-identical to the reference's
-// UCT_search(max_pending_evals=1); parallelism comes from the thousands of trees.
+// One warp owns one tree (one game) and runs its simulations in the reference's order, so no
+// atomics are needed and visit counts are bit-identical to the reference's UCT_search:
+// with max_pending_evals = 1 strictly one simulation after the other; with max_pending_evals = K
+// in the waves the reference's event loop produces (K select_leaf()s leaving their virtual loss
+// behind, a terminal leaf backed up on the spot, then the K expand/backup pairs in the same order;
+// mcts.py:228-242).  Parallelism comes from the thousands of trees.
 //
 // HBM layout per tree t (arena[t] = max_nodes fixed-stride nodes):
 //   node i : [ dbaz_state header 32 B | Child rec[A] 16 B each ]      stride = 32 + 16*A
@@ -29,6 +32,7 @@ enum : uint32_t {
     TF_PREP_PENDING = 4,   // root was unexpanded at begin(): mix priors after its first backup
     TF_ERR_POOL = 8,       // node pool exhausted
     TF_ERR_MOVE = 16,      // advance_roots with an illegal move
+    TF_FIRST_WAVE = 32,    // next wave is the first of this UCT_search: min(max_pending_evals, A) wide (mcts.py:228-229)
 };
 
 struct __align__(64) TreeRec {
@@ -36,8 +40,8 @@ struct __align__(64) TreeRec {
     int32_t root_N;       // TreeRoot.child_number_visits[None]
     float root_W;         // TreeRoot.child_total_value[None] (float32 in effect)
     int32_t sims_left;
-    int32_t leaf;         // node waiting for its evaluation, -1 = none
-    int32_t path_len;
+    int32_t n_pending;    // simulations selected and waiting for their evaluation (<= max_pending)
+    int32_t reserved_;
     uint32_t flags;
     int32_t max_deepness;
     int32_t deepness_correction;
@@ -47,6 +51,27 @@ struct __align__(64) TreeRec {
     unsigned long long total_sims, total_path;
 };
 static_assert(sizeof(TreeRec) == 64, "TreeRec must be 64 bytes");
+
+// the fields a wave carries in registers (first 32 bytes of TreeRec); the statistics stay in memory
+struct TreeHot {
+    int32_t n_nodes, root_N;
+    float root_W;
+    int32_t sims_left, n_pending;
+    uint32_t flags;
+};
+__device__ __forceinline__ TreeHot load_hot(const TreeRec* G) {
+    const uint4 a = reinterpret_cast<const uint4*>(G)[0];
+    const uint4 b = reinterpret_cast<const uint4*>(G)[1];
+    TreeHot T;
+    T.n_nodes = (int)a.x; T.root_N = (int)a.y; T.root_W = __uint_as_float(a.z); T.sims_left = (int)a.w;
+    T.n_pending = (int)b.x; T.flags = b.z;
+    return T;
+}
+__device__ __forceinline__ void store_hot(TreeRec* G, const TreeHot& T) {
+    reinterpret_cast<uint4*>(G)[0] = make_uint4((uint32_t)T.n_nodes, (uint32_t)T.root_N, __float_as_uint(T.root_W), (uint32_t)T.sims_left);
+    reinterpret_cast<uint2*>(G)[2] = make_uint2((uint32_t)T.n_pending, 0u);
+    G->flags = T.flags;
+}
 
 constexpr int PATH_CAP = 128;               // >= number of real edges + 1
 constexpr uint32_t PATH_ROOT = 0x7fffff00u; // parent field of the root's path element
@@ -58,7 +83,8 @@ struct TreeArgs {
     uint32_t* path;       // [n_trees][PATH_CAP]
     const double* lut;    // c0(N) = log((N + base + 1)/base) + cpuct, host libm
     const uint4* act_tab; // [A][2]: the two box masks each action borders (built once per engine)
-    uint4* leaf_hdr;      // [n_trees][2]: copy of the pending leaf's header (saves a dependent load per wave)
+    uint4* pend;          // [max_pending][n_trees][3]: pending leaf {header copy (2 x 16 B), node index, path length}
+    int max_pending;      // lanes of in-flight simulations per tree; row of lane k of tree t = k * n_trees + t
     int lut_size;
     int n_trees;
     int max_nodes;
@@ -195,7 +221,7 @@ __device__ __forceinline__ double ucb_score(double c0, double sq, const Child& c
 // Root prior mix, head of UCT_search (mcts.py:213-226).  Warp-cooperative; `sh` is a per-warp
 // shared scratch of A doubles.  noise == nullptr <=> alpha <= 0.
 template <int APL, int NW>
-__device__ __forceinline__ void root_prior_mix(const Board& b, const TreeArgs& ta, int t, TreeRec& T, const dbaz_state& rh,
+__device__ __forceinline__ void root_prior_mix(const Board& b, const TreeArgs& ta, int t, TreeHot& T, const dbaz_state& rh,
                                                const double* noise, double coeff, double* sh, int lane) {
     const int A = b.A;
     double* rp = ta.root_prior + (int64_t)t * A;
@@ -261,22 +287,40 @@ __device__ __forceinline__ void root_prior_mix(const Board& b, const TreeArgs& t
     __syncwarp();
 }
 
-// Values every lane preloads at kernel entry with loads that do not depend on each other: the
-// tree record, the pending leaf's header copy, its path and its net outputs (one round trip).
+// One pending simulation as the backup needs it: the leaf's header copy, node index, path and net outputs.
+// For lane 0 all of it is preloaded at kernel entry with loads whose addresses depend only on t (one round trip).
 template <int APL>
 struct StepInputs {
     uint4 lh0, lh1;     // pending leaf header
+    int leaf, plen;
     uint32_t pe[PATH_CAP / 32];
     float p[APL];
     float value;
 };
 
-// expand + backup of the pending leaf (mcts.py:116-132 and the prior masking of 188-196)
+template <int APL>
+__device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta, int t, int k, const float* __restrict__ priors,
+                                             const float* __restrict__ values, StepInputs<APL>& in, int lane) {
+    const int64_t row = (int64_t)k * ta.n_trees + t;
+    const uint4* pr = ta.pend + row * 3;
+    in.lh0 = pr[0]; in.lh1 = pr[1];
+    const uint4 m = pr[2];
+    in.leaf = (int)m.x; in.plen = (int)m.y;
+#pragma unroll
+    for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? ta.path[row * PATH_CAP + lane + 32 * i] : 0u;
+#pragma unroll
+    for (int q = 0; q < APL; ++q) { int a = lane + 32 * q; in.p[q] = a < b.A ? priors[row * b.A + a] : 0.0f; }
+    in.value = values[row];
+}
+
+// expand + backup of one pending leaf (mcts.py:116-132 and the prior masking of 188-196).  The virtual loss was
+// subtracted by the selection that produced the path (mcts.py:109), so every path node just gets
+// W = fl32(W + fl32(v*s + 1)) and N += 1.
 template <int APL, int NW>
-__device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArgs& ta, int t, TreeRec& T,
+__device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArgs& ta, int t, TreeHot& T,
                                                    const StepInputs<APL>& in, double* sh, int lane) {
     const int A = b.A;
-    char* lp = node_ptr(ta, t, T.leaf);
+    char* lp = node_ptr(ta, t, in.leaf);
     Hdr lh = unpack_hdr(in.lh0, in.lh1);
     const bool terminal = lh.flags & NF_TERMINAL;
     float value;
@@ -310,7 +354,7 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
         value = in.value;
     } else {
         value = (float)lh.result;  // get_result(): python int 1 / 0
-        if (T.leaf == 0) {
+        if (in.leaf == 0) {
             // a terminal ROOT is re-expanded with np.zeros(A) on every visit (mcts.py:195-198), which
             // also discards whatever the UCT_search head mixed into its child_priors
             double* rp = ta.root_prior + (int64_t)t * A;
@@ -324,9 +368,7 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
         pack_hdr(lh, a4, b4);
         reinterpret_cast<uint4*>(lp)[1] = b4;
     }
-    // backup: every path node gets W += v*s + 1 and N += 1; all but the leaf also carry the
-    // virtual loss subtracted on the way down (W - 1 first, as its own float32 rounding step).
-    const int plen = T.path_len;
+    const int plen = in.plen;
 #pragma unroll
     for (int i = 0; i < PATH_CAP / 32; ++i) {
         const int j = lane + 32 * i;
@@ -335,31 +377,26 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
         const int tp = pe >> 31;
         const float v = (tp == lh.to_play) ? value : -value;
         const float add = __fadd_rn(v, 1.0f);
-        const bool is_leaf = (j == plen - 1);
         if (j == 0) {
-            float W = T.root_W;
-            if (!is_leaf) W = __fsub_rn(W, 1.0f);
-            T.root_W = __fadd_rn(W, add);  // only lane 0 reaches j == 0; T is written back by lane 0
+            T.root_W = __fadd_rn(T.root_W, add);  // only lane 0 reaches j == 0; T is written back by lane 0
             T.root_N += 1;
         } else {
             const int parent = (pe & 0x7fffffffu) >> 8, act = pe & 0xffu;
             float2* cell = reinterpret_cast<float2*>(&node_children(node_ptr(ta, t, parent))[act]);
             float2 wn = *cell;
-            float W = wn.x;
-            if (!is_leaf) W = __fsub_rn(W, 1.0f);
-            wn.x = __fadd_rn(W, add);
+            wn.x = __fadd_rn(wn.x, add);
             wn.y = __int_as_float(__float_as_int(wn.y) + 1);
             *cell = wn;
         }
     }
     if (lane == 0) {
-        T.terminal_count += terminal ? 1 : 0;
-        T.max_deepness = max(T.max_deepness, lh.depth);
-        T.total_term += terminal ? 1 : 0;
-        T.total_sims += 1;
-        T.total_path += plen;
+        // tree statistics are only ever touched here: update them in place instead of carrying them in registers
+        TreeRec* G = ta.trees + t;
+        if (terminal) { G->terminal_count += 1; G->total_term += 1; }
+        if (lh.depth > G->max_deepness) G->max_deepness = lh.depth;
+        G->total_sims += 1;
+        G->total_path += plen;
     }
-    T.leaf = -1;
 }
 
 // Warp argmax of (score, lowest action id wins ties) with three REDUX operations on an
@@ -378,16 +415,22 @@ __device__ __forceinline__ int warp_argmax(double best, int best_a) {
     return (int)__reduce_min_sync(0xffffffffu, c2 ? (unsigned)best_a : 0x7fffffffu);
 }
 
-// select_leaf with lazy child creation (mcts.py:105-114).  Returns the leaf kind
-// (1 = needs evaluation, 2 = terminal) and leaves the leaf header in `leaf_hdr`.
+// select_leaf with lazy child creation (mcts.py:105-114).  Returns the leaf kind (1 = needs evaluation,
+// 2 = terminal, 0 = node pool exhausted); leaf header / index / path length are left in `out`, the path itself in
+// `path` (global, read back by the backup).  VIRTUAL_LOSS is subtracted from every node left behind (mcts.py:109):
+// the root's own W lives in the tree record (lane 0), any other node's in its parent's child record, which the lane
+// that owned the winning action still holds from the previous level.
 template <int APL, int NW>
-__device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, int t, TreeRec& T,
-                                           const LaneActions<APL, NW>& la, Hdr& leaf_hdr, int lane) {
+__device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, int t, TreeHot& T,
+                                           const LaneActions<APL, NW>& la, StepInputs<APL>& out, uint32_t* __restrict__ path,
+                                           int lane) {
     const int A = b.A;
     const double* rp = ta.root_prior + (int64_t)t * A;
     int cur = 0, curN = T.root_N, depth = 0;
-    uint32_t* path = ta.path + (int64_t)t * PATH_CAP;  // published for the backup that follows the evaluation
     int leaf = -1;
+    Hdr leaf_hdr;
+    float* vl_cell = nullptr;  // W of the current node's own record (valid on the lane that owned the action)
+    float vl_w = 0.0f;
     while (true) {
         char* np = node_ptr(ta, t, cur);
         // header and child records are fetched together; an unexpanded / terminal node has garbage
@@ -411,6 +454,9 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
         const bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
         if (depth == 0 && lane == 0) path[0] = PATH_ROOT | ((uint32_t)h.to_play << 31);
         if (!interior) { leaf = cur; leaf_hdr = h; break; }
+        // current.total_value -= VIRTUAL_LOSS
+        if (depth == 0) { if (lane == 0) T.root_W = __fsub_rn(T.root_W, 1.0f); }
+        else if (vl_cell) *vl_cell = __fsub_rn(vl_w, 1.0f);
 
         const Mask<NW> e = hdr_edges<NW>(h);
         const double sq = __dsqrt_rn((double)curN);
@@ -432,9 +478,13 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
         const int a = warp_argmax(best, best_a);  // a non-terminal node always has a legal move
         const int owner = a & 31, kk = a >> 5;
         int child = 0, childN = 0, ncl = 0;
+        vl_cell = nullptr;
 #pragma unroll
         for (int k = 0; k < APL; ++k)
-            if (k == kk) { child = (int)craw[k].w; childN = (int)craw[k].y; ncl = la.closes(k, e, lane + 32 * k); }
+            if (k == kk) {
+                child = (int)craw[k].w; childN = (int)craw[k].y; ncl = la.closes(k, e, lane + 32 * k);
+                if (lane == owner) { vl_cell = &node_children(np)[a].W; vl_w = __uint_as_float(craw[k].x); }
+            }
         child = __shfl_sync(0xffffffffu, child, owner);
         childN = __shfl_sync(0xffffffffu, childN, owner);
         ncl = __shfl_sync(0xffffffffu, ncl, owner);
@@ -462,8 +512,9 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
         }
         cur = child; curN = childN;
     }
-    T.leaf = leaf;
-    T.path_len = depth + 1;
+    pack_hdr(leaf_hdr, out.lh0, out.lh1);
+    out.leaf = leaf;
+    out.plen = depth + 1;
     return (leaf_hdr.flags & NF_TERMINAL) ? 2 : 1;
 }
 
@@ -477,9 +528,10 @@ k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * TREE_WARPS + warp;
     if (t >= ta.n_trees) return;
-    TreeRec T = ta.trees[t];
+    TreeHot T = load_hot(ta.trees + t);
     const int nr = num_reads[t];
-    T.leaf = -1;
+    T.n_pending = 0;
+    T.flags &= ~TF_FIRST_WAVE;
     if (nr == -2) {
         // only the initial _search() of an unexpanded root (mcts.py:207-208), no prior mix: lets a host
         // caller draw its Dirichlet noise AFTER the root evaluation, in the reference's RNG order
@@ -494,17 +546,19 @@ k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, cons
         if (rh.flags & NF_EXPANDED) {
             root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh_all[warp], lane);
             T.sims_left = nr;
+            T.flags |= TF_FIRST_WAVE;
         } else {
             T.flags |= TF_PREP_PENDING;  // mcts.py:207-208: one extra _search() first
             T.sims_left = nr + 1;
         }
     }
-    if (lane == 0) ta.trees[t] = T;
+    if (lane == 0) store_hot(ta.trees + t, T);
 }
 
 template <int APL, int NW>
 __global__ void __launch_bounds__(TREE_WARPS * 32, APL == 1 ? 7 : (APL == 2 ? 5 : 3))
-k_search_step(Board b, TreeArgs ta, const float* __restrict__ priors, const float* __restrict__ values,
+k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this search, <= ta.max_pending */,
+              const float* __restrict__ priors, const float* __restrict__ values,
               const double* __restrict__ noise, double coeff, void* __restrict__ planes, int dtype, int layout,
               dbaz_state* __restrict__ leaf_states, int8_t* __restrict__ leaf_kind) {
     __shared__ double sh_all[TREE_WARPS][DBAZ_MAX_ACTIONS];
@@ -512,57 +566,74 @@ k_search_step(Board b, TreeArgs ta, const float* __restrict__ priors, const floa
     const int t = blockIdx.x * TREE_WARPS + warp;
     if (t >= ta.n_trees) return;
     // ---- one round trip: everything whose address depends only on t
-    TreeRec T = ta.trees[t];
+    TreeHot T = load_hot(ta.trees + t);
     StepInputs<APL> in;
-    in.lh0 = ta.leaf_hdr[2 * t]; in.lh1 = ta.leaf_hdr[2 * t + 1];
-#pragma unroll
-    for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? ta.path[(int64_t)t * PATH_CAP + lane + 32 * i] : 0u;
-#pragma unroll
-    for (int k = 0; k < APL; ++k) { int a = lane + 32 * k; in.p[k] = a < b.A ? priors[(int64_t)t * b.A + a] : 0.0f; }
-    in.value = values[t];
+    load_pending<APL>(b, ta, t, 0, priors, values, in, lane);
     LaneActions<APL, NW> la;
     la.load(b, ta.act_tab, lane);
 
-    if (T.leaf < 0 && T.sims_left <= 0) {  // idle tree
-        if (leaf_kind && lane == 0) leaf_kind[t] = 0;
+    if (T.n_pending <= 0 && T.sims_left <= 0) {  // idle tree
+        if (leaf_kind) for (int r = lane; r < pending; r += 32) leaf_kind[(int64_t)r * ta.n_trees + t] = 0;
         return;
     }
     double* sh = sh_all[warp];
-    if (T.leaf >= 0) {
+    // ---- the evaluations of the previous wave come back: expand + backup, in selection order
+    const int n_back = T.n_pending;
+    for (int k = 0; k < n_back; ++k) {
+        if (k > 0) { __syncwarp(); load_pending<APL>(b, ta, t, k, priors, values, in, lane); }
         tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane);
-        // lane 0 owns the authoritative TreeRec; re-broadcast the field the other lanes need
+    }
+    T.n_pending = 0;
+    if (n_back > 0) {
+        // lane 0 owns the authoritative TreeRec; re-broadcast what the other lanes need
         T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
         __syncwarp();
         if (T.flags & TF_PREP_PENDING) {
             dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
             root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
+            T.flags |= TF_FIRST_WAVE;
         }
     }
-    int kind = 0;
-    if (T.sims_left > 0) {
-        Hdr lh;
-        __syncwarp();  // backup stores above must be visible to the selection loads below
-        kind = tree_select<APL, NW>(b, ta, t, T, la, lh, lane);
-        if (kind) {
-            T.sims_left -= 1;
-            const Mask<NW> e = hdr_edges<NW>(lh);
-            write_planes_warp<NW>(b, e, (int)(int8_t)(lh.to_play ? lh.btc1 : lh.btc0), planes, t, dtype, layout, lane);
-            if (lane == 0) {
-                uint4 a4, b4;
-                pack_hdr(lh, a4, b4);
-                ta.leaf_hdr[2 * t] = a4; ta.leaf_hdr[2 * t + 1] = b4;
-                if (leaf_states) {
-                    Hdr pub = lh;
-                    pub.flags = 0; pub.depth = 0; pub.parent = -1; pub.parent_action = -1;
-                    store_hdr_regs(reinterpret_cast<char*>(&leaf_states[t]), pub);
-                }
+    // ---- this wave's selections.  Width: 1 while the root still awaits its own expansion (mcts.py:207-208), else
+    // min(max_pending_evals, A) for the first wave of a search and max_pending_evals afterwards (mcts.py:228-236).
+    int width = pending;
+    if (T.flags & TF_PREP_PENDING) width = 1;
+    else if (T.flags & TF_FIRST_WAVE) { width = min(pending, b.A); T.flags &= ~TF_FIRST_WAVE; }
+    const int n_sel = min(width, T.sims_left);
+    int n_out = 0;
+    for (int k = 0; k < n_sel; ++k) {
+        __syncwarp();  // stores of the backups / previous selections must be visible to this selection's loads
+        const int64_t row = (int64_t)n_out * ta.n_trees + t;
+        uint32_t* path = ta.path + row * PATH_CAP;
+        const int kind = tree_select<APL, NW>(b, ta, t, T, la, in, path, lane);
+        if (!kind) break;  // node pool exhausted
+        T.sims_left -= 1;
+        if (kind == 2) {
+            // a terminal leaf never awaits the net: its simulation completes before the next one is selected
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? path[lane + 32 * i] : 0u;
+            tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane);
+            T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
+            continue;
+        }
+        const Hdr lh = unpack_hdr(in.lh0, in.lh1);
+        write_planes_warp<NW>(b, hdr_edges<NW>(lh), (int)(int8_t)(lh.to_play ? lh.btc1 : lh.btc0), planes, row, dtype, layout, lane);
+        if (lane == 0) {
+            uint4* pr = ta.pend + row * 3;
+            pr[0] = in.lh0; pr[1] = in.lh1; pr[2] = make_uint4((uint32_t)in.leaf, (uint32_t)in.plen, 0u, 0u);
+            if (leaf_states) {
+                Hdr pub = lh;
+                pub.flags = 0; pub.depth = 0; pub.parent = -1; pub.parent_action = -1;
+                store_hdr_regs(reinterpret_cast<char*>(&leaf_states[row]), pub);
             }
+            if (leaf_kind) leaf_kind[row] = 1;
         }
+        ++n_out;
     }
-    if (lane == 0) {
-        ta.trees[t] = T;
-        if (leaf_kind) leaf_kind[t] = (int8_t)kind;
-    }
+    T.n_pending = n_out;
+    if (leaf_kind) for (int r = lane; r < pending; r += 32) if (r >= n_out) leaf_kind[(int64_t)r * ta.n_trees + t] = 0;
+    if (lane == 0) store_hot(ta.trees + t, T);
 }
 
 // UCT_search's time limit (mcts.py:232-233): launch no further simulations; pending leaves still back up
@@ -586,7 +657,7 @@ __global__ void k_reset_roots(Board b, TreeArgs ta, const dbaz_state* __restrict
     s.parent = -1; s.parent_action = -1; s.result = (int16_t)r;
     store_hdr(node_ptr(ta, t, 0), s);
     TreeRec T;
-    T.n_nodes = 1; T.root_N = 0; T.root_W = 0.0f; T.sims_left = 0; T.leaf = -1; T.path_len = 0; T.flags = 0;
+    T.n_nodes = 1; T.root_N = 0; T.root_W = 0.0f; T.sims_left = 0; T.n_pending = 0; T.reserved_ = 0; T.flags = 0;
     T.max_deepness = 0; T.deepness_correction = 0; T.terminal_count = 0; T.tree_size = 0; T.total_term = 0;
     T.total_sims = 0; T.total_path = 0;
     ta.trees[t] = T;
@@ -721,9 +792,9 @@ k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reu
         }
     }
     if (tid == 0) {
-        T.root_N = 0; T.root_W = 0.0f; T.leaf = -1; T.path_len = 0; T.sims_left = 0;
+        T.root_N = 0; T.root_W = 0.0f; T.n_pending = 0; T.sims_left = 0;
         T.max_deepness = 0; T.terminal_count = 0;
-        T.flags &= ~(TF_PRIOR_SET | TF_PRIOR_F64 | TF_PREP_PENDING);
+        T.flags &= ~(TF_PRIOR_SET | TF_PRIOR_F64 | TF_PREP_PENDING | TF_FIRST_WAVE);
         ta.trees[t] = T;
     }
 }

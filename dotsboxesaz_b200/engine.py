@@ -29,7 +29,7 @@ class Engine:
     States are device tensors of shape [n, 4] int64 (32 packed bytes each, see STATE_DTYPE).
     """
 
-    def __init__(self, board=(3, 3), n_games=1, max_nodes=8192, cpuct=(1.25, 19652), device=None, lut_size=0):
+    def __init__(self, board=(3, 3), n_games=1, max_nodes=8192, cpuct=(1.25, 19652), device=None, lut_size=0, max_pending=1):
         if not torch.cuda.is_available():
             raise RuntimeError("dotsboxesaz_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _capi.load()
@@ -38,7 +38,7 @@ class Engine:
             raise RuntimeError("dotsboxesaz_b200 engines live on CUDA devices only")
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", dev_index)
-        cfg = _capi.Config(1, dev_index, int(board[0]), int(board[1]), int(n_games), int(max_nodes), int(lut_size), 0,
+        cfg = _capi.Config(1, dev_index, int(board[0]), int(board[1]), int(n_games), int(max_nodes), int(lut_size), int(max_pending),
                            float(cpuct[0]), float(cpuct[1]))
         h = C.c_void_p()
         torch.cuda.init()
@@ -47,15 +47,19 @@ class Engine:
         self._h = h
         info = (C.c_int32 * 8)()
         self.lib.dbaz_engine_info(self._h, info)
-        self.L, self.C, self.A, self.F, self.n_games, self.max_nodes, self.node_bytes, self.n_sms = list(info)
+        self.L, self.C, self.A, self.F, self.n_games, self.max_nodes, self.node_bytes, self.max_pending = list(info)
         self.rows, self.cols = self.L + 1, self.C + 1
         self.cpuct = (float(cpuct[0]), float(cpuct[1]))
-        # search I/O buffers (fixed addresses, so the wave loop can be captured in a CUDA graph)
-        self.priors = torch.zeros((n_games, self.A), dtype=torch.float32, device=self.device)
-        self.values = torch.zeros((n_games,), dtype=torch.float32, device=self.device)
-        self.leaf_states = torch.zeros((n_games, 4), dtype=torch.int64, device=self.device)
-        self.leaf_kind = torch.zeros((n_games,), dtype=torch.int8, device=self.device)
-        self.planes = None
+        # search I/O buffers (fixed addresses, so the wave loop can be captured in a CUDA graph).  One row per
+        # in-flight simulation: row of slot k of tree t = k * n_games + t; a search with max_pending_evals = K uses
+        # the first K * n_games rows (`self.n_rows`), evaluators work on the `[:n_rows]` views below.
+        cap = n_games * self.max_pending
+        self._priors = torch.zeros((cap, self.A), dtype=torch.float32, device=self.device)
+        self._values = torch.zeros((cap,), dtype=torch.float32, device=self.device)
+        self._leaf_states = torch.zeros((cap, 4), dtype=torch.int64, device=self.device)
+        self._leaf_kind = torch.zeros((cap,), dtype=torch.int8, device=self.device)
+        self.pending = 1
+        self._planes = None
         self._plane_cfg = None
         self._noise = None  # keeps the caller's noise buffer alive while the engine may read it
         self._num_reads = torch.zeros((n_games,), dtype=torch.int32, device=self.device)
@@ -64,6 +68,7 @@ class Engine:
         self._graphs = {}
         self.n_launches = 0  # engine kernels enqueued (graph replays count the kernels they contain)
         self.set_planes(torch.float32, channels_last=False)
+        self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
     # ------------------------------------------------------------ plumbing
     def close(self):
@@ -98,17 +103,43 @@ class Engine:
             self._ck(self.lib.dbaz_engine_set_cpuct(self._h, cpuct[0], cpuct[1]))
             self.cpuct = cpuct
 
+    @property
+    def n_rows(self):
+        """Leaf rows of the current search: max_pending_evals * n_games."""
+        return self.pending * self.n_games
+
+    @property
+    def priors(self):
+        return self._priors[:self.n_rows]
+
+    @property
+    def values(self):
+        return self._values[:self.n_rows]
+
+    @property
+    def leaf_states(self):
+        return self._leaf_states[:self.n_rows]
+
+    @property
+    def leaf_kind(self):
+        return self._leaf_kind[:self.n_rows]
+
+    @property
+    def planes(self):
+        return self._planes[:self.n_rows]
+
     def set_planes(self, dtype=torch.float32, channels_last=False):
         """Choose dtype/layout of the leaf feature tensor the select kernel writes (the net's input)."""
         cfg = (dtype, bool(channels_last))
         if cfg != self._plane_cfg:
+            cap = self.n_games * self.max_pending
             if channels_last:
-                base = torch.zeros((self.n_games, self.rows, self.cols, 3), dtype=dtype, device=self.device)
-                self.planes = base.permute(0, 3, 1, 2)  # logical NCHW view over NHWC memory
+                base = torch.zeros((cap, self.rows, self.cols, 3), dtype=dtype, device=self.device)
+                self._planes = base.permute(0, 3, 1, 2)  # logical NCHW view over NHWC memory
                 self._planes_base = base
             else:
-                self.planes = torch.zeros((self.n_games, 3, self.rows, self.cols), dtype=dtype, device=self.device)
-                self._planes_base = self.planes
+                self._planes = torch.zeros((cap, 3, self.rows, self.cols), dtype=dtype, device=self.device)
+                self._planes_base = self._planes
             self._plane_cfg = cfg
         return self.planes
 
@@ -228,9 +259,13 @@ class Engine:
         self._noise = None
         self._ck(self.lib.dbaz_search_reset_roots(self._h, _ptr(states), self._stream()))
 
-    def begin(self, num_reads, noise=None, coeff=0.0):
+    def begin(self, num_reads, noise=None, coeff=0.0, pending=1):
         """Head of UCT_search (mcts.py:205-229).  num_reads: int or int32[n_games] (-1 = idle tree).
-        noise: float64 [n_games, A] Dirichlet sample times legal mask, or None (alpha <= 0)."""
+        noise: float64 [n_games, A] Dirichlet sample times legal mask, or None (alpha <= 0).
+        pending: max_pending_evals, simulations in flight per tree (<= the engine's max_pending)."""
+        if not 1 <= int(pending) <= self.max_pending:
+            raise ValueError("pending must be in [1, %d] (Engine(max_pending=...))" % self.max_pending)
+        self.pending = int(pending)
         if isinstance(num_reads, int):
             self._num_reads.fill_(num_reads)
         else:
@@ -240,54 +275,61 @@ class Engine:
             if noise.shape != (self.n_games, self.A):
                 raise ValueError("noise must have shape [n_games, A]")
         self._noise = noise
-        self._ck(self.lib.dbaz_search_begin(self._h, _ptr(self._num_reads), _ptr(noise), float(coeff), self._stream()))
+        self._ck(self.lib.dbaz_search_begin(self._h, _ptr(self._num_reads), self.pending, _ptr(noise), float(coeff), self._stream()))
 
     def step(self):
         """One lock-step wave: backup the leaves evaluated into self.priors/self.values, then select the
         next leaf of every tree into self.planes / self.leaf_states / self.leaf_kind."""
         dtype, cl = self._plane_cfg
-        self._ck(self.lib.dbaz_search_step(self._h, _ptr(self.priors), _ptr(self.values), _ptr(self._planes_base),
-                                           _DTYPE_CODE[dtype], _capi.NHWC if cl else _capi.NCHW, _ptr(self.leaf_states),
-                                           _ptr(self.leaf_kind), self._stream()))
+        self._ck(self.lib.dbaz_search_step(self._h, _ptr(self._priors), _ptr(self._values), _ptr(self._planes_base),
+                                           _DTYPE_CODE[dtype], _capi.NHWC if cl else _capi.NCHW, _ptr(self._leaf_states),
+                                           _ptr(self._leaf_kind), self._stream()))
 
     def step_flush(self):
         """Stop launching simulations (UCT_search's time limit) and back up the pending leaves."""
         self._ck(self.lib.dbaz_search_stop(self._h, self._stream()))
         self.step()
 
-    def run_search(self, num_reads, evaluator, noise=None, coeff=0.0, max_reads=None, graph_waves=0):
+    def run_search(self, num_reads, evaluator, noise=None, coeff=0.0, max_reads=None, graph_waves=0, pending=1):
         """UCT_search for all trees.  `evaluator(engine)` must fill engine.priors / engine.values for the
         leaves in engine.planes / engine.leaf_states, on the current stream, without host sync.
 
+        pending: max_pending_evals (simulations in flight per tree, see begin()).
         graph_waves > 0: `graph_waves` consecutive [step kernel -> evaluator] waves are captured once in a
         CUDA graph and replayed, so the 800-wave inner loop costs one launch per `graph_waves` waves.
         Surplus waves at the end of the last replay are no-ops for trees that have finished."""
         if max_reads is None:
             max_reads = int(num_reads) if isinstance(num_reads, int) else int(torch.as_tensor(num_reads).max())
-        waves = max(max_reads, 0) + 1  # +1: an unexpanded root takes one extra simulation
+        pending = int(pending)
+        self.pending = pending
+        # one wave for the expansion of an unexpanded root, one first wave of min(pending, A) simulations, then
+        # `pending` per wave (terminal leaves complete inside the step and only make this an upper bound)
+        first = min(pending, self.A)
+        waves = 2 + max(0, -(-(max(max_reads, 0) - first) // pending))
         if graph_waves > 0:
             if noise is not None:  # a stable address for the captured step kernel
                 if self._noise_buf is None:
                     self._noise_buf = torch.zeros((self.n_games, self.A), dtype=torch.float64, device=self.device)
                 self._noise_buf.copy_(torch.as_tensor(noise, dtype=torch.float64).reshape(self.n_games, self.A))
                 noise = self._noise_buf
-            key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg)
+            key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, pending)
             if key not in self._graphs:
-                self._graphs[key] = self._capture(evaluator, graph_waves, noise, coeff)
-            self.begin(num_reads, noise, coeff)
-            g = self._graphs[key]
+                # the evaluator is stored next to its graph: a live reference keeps id() from being recycled
+                self._graphs[key] = (self._capture(evaluator, graph_waves, noise, coeff, pending), evaluator)
+            self.begin(num_reads, noise, coeff, pending)
+            g = self._graphs[key][0]
             per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
             for _ in range((waves + graph_waves - 1) // graph_waves):
                 g.replay()
                 self.n_launches += graph_waves * per_wave
         else:
-            self.begin(num_reads, noise, coeff)
+            self.begin(num_reads, noise, coeff, pending)
             for _ in range(waves):
                 self.step()
                 evaluator(self)
         self.step()  # flush the last backup
 
-    def _capture(self, evaluator, graph_waves, noise, coeff):
+    def _capture(self, evaluator, graph_waves, noise, coeff, pending=1):
         # warm up the evaluator alone (allocator, cuDNN heuristics); no leaf is pending between searches,
         # so overwriting priors/values here is harmless
         cur = torch.cuda.current_stream(self.device)
@@ -300,7 +342,7 @@ class Engine:
         torch.cuda.synchronize(self.device)
         # the captured step kernels carry the noise pointer / coeff of begin(); bind them first
         self._noise = noise
-        self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), _ptr(noise), float(coeff), self._stream())
+        self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), int(pending), _ptr(noise), float(coeff), self._stream())
         g = torch.cuda.CUDAGraph()
         n0 = self.n_launches
         with torch.cuda.graph(g):

@@ -7,10 +7,11 @@
 Each root owns one single-tree engine handle; select / lazy child creation / expand / backup /
 re-rooting all run in the sm_100a kernels (dbaz_search_step, dbaz_search_advance_roots).  The only
 host work per simulation is what the reference's API forces: awaiting the caller's Python
-`async_nn(game_state)` and handing its (p, v) back.  Simulations of one tree are strictly
-sequential, i.e. the reference's behaviour at max_pending_evals=1 (the setting its own test uses,
-test/mcts_tests.py:100, and the only one for which it is reproducible); `max_pending_evals` is
-accepted and ignored.  Throughput comes from dotsboxesaz_b200.self_play.BatchedSelfPlay, which runs
+`async_nn(game_state)` and handing its (p, v) back.  With max_pending_evals = 1 the simulations are
+strictly sequential; with K the engine runs the waves the reference's event loop runs when the net
+suspends each _search() once (K select_leaf()s leaving their virtual loss behind, then the K
+expand/backup pairs in order) and awaits the K `async_nn` calls concurrently, exactly what a
+batching proxy needs.  Throughput comes from dotsboxesaz_b200.self_play.BatchedSelfPlay, which runs
 thousands of such trees in lock-step against a device-resident net.
 
 Node objects are views: the CURRENT root reads live engine state; after init_mcts_tree() the old
@@ -30,13 +31,14 @@ from .dots_boxes.dots_boxes_game import BoxesState
 TreeStats = collections.namedtuple("TreeStats", ["max_deepness", "tree_size", "terminal_count", "q_value"])
 VIRTUAL_LOSS = 1
 DEFAULT_MAX_NODES = 32768
+DEFAULT_MAX_PENDING = 64  # configuration.py:35 (max_async_searches)
 
 _POOL = collections.defaultdict(list)
 
 
 def _acquire(dim):
     pool = _POOL[dim]
-    return pool.pop() if pool else _engine.Engine(dim, n_games=1, max_nodes=DEFAULT_MAX_NODES)
+    return pool.pop() if pool else _engine.Engine(dim, n_games=1, max_nodes=DEFAULT_MAX_NODES, max_pending=DEFAULT_MAX_PENDING)
 
 
 def _release(dim, eng):
@@ -178,25 +180,34 @@ async def UCT_search(root_node, num_reads, async_nn, cpuct=(1.25, 19652), max_pe
     eng.set_cpuct(cpuct)
 
     dev = eng.device
+    K = max(1, min(int(max_pending_evals), eng.max_pending))
+    import asyncio
 
-    async def drain():
-        while True:
+    async def drain(n_sims, pending):
+        """Run waves until the budget is spent: every wave hands the caller's net the leaves of up to `pending`
+        simulations at once (awaited concurrently) and feeds the answers to the next wave's backups."""
+        first = min(pending, eng.A)
+        waves = 2 + max(0, -(-(n_sims - first) // pending))  # upper bound, see Engine.run_search
+        for _ in range(waves):
             eng.step()
-            kind = int(eng.leaf_kind[0])  # device -> host sync: the caller's Python net must see the leaf
-            if kind == 0:
-                return
-            if kind == 1:
-                leaf = BoxesState.from_packed(eng.states_to_numpy(eng.leaf_states))
-                p, v = await async_nn(leaf)
-                eng.priors.copy_(torch.as_tensor(np.asarray(p, dtype=np.float32)).reshape(1, -1).to(dev))
-                eng.values.copy_(torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(-1)[:1].to(dev))
+            kinds = eng.leaf_kind.cpu().numpy()  # device -> host sync: the caller's Python net must see the leaves
+            rows = np.flatnonzero(kinds == 1)
+            if rows.size:
+                packed = eng.states_to_numpy(eng.leaf_states)
+                outs = await asyncio.gather(*(async_nn(BoxesState.from_packed(packed[r])) for r in rows))
+                p = np.stack([np.asarray(o[0], dtype=np.float32).reshape(-1) for o in outs])
+                v = np.asarray([np.asarray(o[1], dtype=np.float32).reshape(-1)[0] for o in outs], dtype=np.float32)
+                idx = torch.from_numpy(rows).to(dev)
+                eng.priors.index_copy_(0, idx, torch.from_numpy(p).to(dev))
+                eng.values.index_copy_(0, idx, torch.from_numpy(v).to(dev))
             if time.time() > end_time:
-                eng.step_flush()  # mcts.py:232-233: launch no more simulations; back up the pending one
+                eng.step_flush()  # mcts.py:232-233: launch no more simulations; back up the pending ones
                 return
+        eng.step()  # flush the last backups
 
     if not root_node.is_expanded:
-        eng.begin(-2)  # mcts.py:207-208, before the noise is drawn (keeps the global RNG order)
-        await drain()
+        eng.begin(-2, pending=1)  # mcts.py:207-208, before the noise is drawn (keeps the global RNG order)
+        await drain(1, 1)
     alpha, coeff = dirichlet
     noise = None
     if alpha > 0:
@@ -206,8 +217,8 @@ async def UCT_search(root_node, num_reads, async_nn, cpuct=(1.25, 19652), max_pe
         conc[conc == 0] = 1e-60
         noise = np.random.dirichlet(conc * alpha, 1).ravel() * valid
         noise = torch.from_numpy(noise).reshape(1, -1)
-    eng.begin(int(num_reads), noise, float(coeff))
-    await drain()
+    eng.begin(int(num_reads), noise, float(coeff), pending=K)
+    await drain(int(num_reads), K)
     eng.status()
     return root_node.child_number_visits
 

@@ -353,7 +353,7 @@ class FusedSimpleNN:
         if use_stem and dtype in (torch.bfloat16, torch.float16) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5)):
             s0, t0 = _bn_affine(model.bn0)
             self.stem = _stem_tables(model.conv0, engine.rows, engine.cols) + (s0, t0)
-            self.stem_out = torch.empty((engine.n_games, engine.rows, engine.cols, model.conv0.out_channels), dtype=dtype, device=dev)
+            self.stem_out = torch.empty((engine.n_games * engine.max_pending, engine.rows, engine.cols, model.conv0.out_channels), dtype=dtype, device=dev)
         for i in range(1 if self.stem is not None else 0, 5):
             conv, bn = getattr(model, f"conv{i}"), getattr(model, f"bn{i}")
             w = conv.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last)
@@ -378,7 +378,7 @@ class FusedSimpleNN:
     def __call__(self, eng):
         if self.stem is not None:
             w01, bp, k2, s0, t0 = self.stem
-            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out, mode=0).permute(0, 3, 1, 2)
+            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out[:eng.n_rows], mode=0).permute(0, 3, 1, 2)
         else:
             x = eng.planes
         for w, b, s, t, pad in self.convs:
@@ -420,7 +420,7 @@ class FusedResNetZero:
         if (use_stem and dtype in (torch.bfloat16, torch.float16) and not isinstance(c0, nn.Sequential) and c0.padding == (1, 1)
                 and c0.out_channels in (8, 16, 32, 64, 128, 256) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5))):
             self.fused_stem = _stem_tables(c0, engine.rows, engine.cols, s_in, t_in) + (self.stem[2], self.stem[3])
-            self.stem_out = torch.empty((engine.n_games, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
+            self.stem_out = torch.empty((engine.n_games * engine.max_pending, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
         self.blocks = []
         for blk in model.resnet.resblocks:
             if blk.inner_conv is not None:
@@ -444,7 +444,7 @@ class FusedResNetZero:
         self.v_b = vh.fc1.bias.detach().to(dtype)
         self.A = A
         self.ld = (A + 1 + 7) // 8 * 8
-        self.logits = torch.zeros((engine.n_games, self.ld), dtype=dtype, device=dev)
+        self.logits = torch.zeros((engine.n_games * engine.max_pending, self.ld), dtype=dtype, device=dev)
         self.engine_launches = 2 + 2 * len(self.blocks) + 2
         engine.set_planes(dtype, channels_last=True)
 
@@ -452,7 +452,7 @@ class FusedResNetZero:
     def __call__(self, eng):
         if self.fused_stem is not None:
             w01, bp, k2, s0, t0 = self.fused_stem
-            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out, mode=1).permute(0, 3, 1, 2)
+            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out[:eng.n_rows], mode=1).permute(0, 3, 1, 2)
         else:
             x = eng.planes * self.in_scale + self.in_shift
             w, b, s, t, pad = self.stem
@@ -468,9 +468,10 @@ class FusedResNetZero:
         h = F.conv2d(x, hw_, None)
         eng.nn_epilogue(h.permute(0, 2, 3, 1), hb, hs, ht, mode=1)
         out = torch.addmm(self.head_b, h.permute(0, 2, 3, 1).reshape(h.shape[0], -1), self.head_w)
-        self.logits[:, :self.A] = out[:, :self.A]
-        self.logits[:, self.A:self.A + 1] = torch.addmm(self.v_b, F.relu(out[:, self.A:]), self.v_w)
-        eng.nn_heads(self.logits)
+        logits = self.logits[:eng.n_rows]
+        logits[:, :self.A] = out[:, :self.A]
+        logits[:, self.A:self.A + 1] = torch.addmm(self.v_b, F.relu(out[:, self.A:]), self.v_w)
+        eng.nn_heads(logits)
 
 
 def make_evaluator(model, engine, dtype=torch.bfloat16):

@@ -32,6 +32,7 @@ extern "C" {
 #define DBAZ_ABI_VERSION 1
 #define DBAZ_MAX_ACTIONS 128 /* A = 2*(L+1)*(C+1) <= 128, i.e. boards up to 7x7 boxes */
 #define DBAZ_RESULT_NONE 2   /* get_result() is None */
+#define DBAZ_MAX_PENDING 128 /* upper bound of max_pending_evals per tree */
 
 /* Bit-packed game state, 32 bytes (dots_boxes_game.py:13, __slots__ hash/board/
  * just_played/to_play/boxes_to_close).  Bit a of `edges` is set iff
@@ -55,7 +56,7 @@ typedef struct dbaz_config {
     int32_t n_games;       /* concurrent games == trees on this GPU */
     int32_t max_nodes;     /* node-pool capacity per tree (>= sims per move + retained subtree) */
     int32_t lut_size;      /* entries of the host-libm log table for the PUCT constant; 0 = 65536 */
-    int32_t reserved;
+    int32_t max_pending;   /* largest max_pending_evals (in-flight simulations per tree) a search may ask for; 0 = 1 */
     double cpuct;          /* UCTNode.CPUCT (mcts.py:44) */
     double cpuct_base;     /* UCTNode.CPUCT_BASE (mcts.py:45) */
 } dbaz_config;
@@ -75,7 +76,7 @@ int dbaz_sizeof_state(void);
 int dbaz_engine_create(const dbaz_config *cfg, dbaz_engine **out);
 void dbaz_engine_destroy(dbaz_engine *e);
 const char *dbaz_last_error(const dbaz_engine *e); /* e may be NULL: error of the last failed create */
-int dbaz_engine_info(const dbaz_engine *e, int32_t *out8); /* {L, C, A, F=3*(L+1)*(C+1), n_games, max_nodes, node_bytes, n_sms} */
+int dbaz_engine_info(const dbaz_engine *e, int32_t *out8); /* {L, C, A, F=3*(L+1)*(C+1), n_games, max_nodes, node_bytes, max_pending} */
 /* mcts.py:205 -- UCT_search assigns UCTNode.CPUCT/CPUCT_BASE on every call (host sync: rebuilds the log table) */
 int dbaz_engine_set_cpuct(dbaz_engine *e, double cpuct, double cpuct_base);
 
@@ -106,18 +107,25 @@ int dbaz_game_random_rollout(dbaz_engine *e, dbaz_state *states, uint64_t seed, 
 int dbaz_search_reset_roots(dbaz_engine *e, const dbaz_state *root_states, uint64_t stream);
 /* Head of UCT_search (mcts.py:205-229).  num_reads int32[n_games] (-1 = tree idle this search;
  * -2 = only the initial _search() of an unexpanded root, without the prior mix).
- * noise float64[n_games][A] = Dirichlet sample already multiplied by the legal mask
- * (mcts.py:220-223) or NULL when alpha <= 0; coeff = dirichlet[1].  Unexpanded roots get the extra
- * initial _search() (mcts.py:207-208) before the prior mix, exactly as the reference orders it.
- * The noise buffer must stay valid until the first dbaz_search_step() after it has returned. */
-int dbaz_search_begin(dbaz_engine *e, const int32_t *num_reads, const double *noise, double coeff, uint64_t stream);
-/* One lock-step wave = for every tree: [expand + backup of the pending leaf using priors/values]
- * then [select_leaf + lazy child creation + feature gather] (mcts.py:105-132,184-199).
- *   priors float32[n_games][A], values float32[n_games]: net outputs for the leaves emitted by the
- *   PREVIOUS step (probabilities, i.e. exp(log_softmax), and tanh value; nn.py:155-160).
- *   planes: net input for the leaves selected by THIS step; leaf_states (may be NULL): their packed
- *   states; leaf_kind int8[n_games] (may be NULL): 0 = no leaf (tree idle/done), 1 = needs eval,
- *   2 = terminal (net output ignored). */
+ * pending = max_pending_evals (1 <= pending <= cfg.max_pending): simulations in flight per tree.  With 1 the
+ * simulations of a tree are strictly sequential; with K the engine reproduces the waves the reference's event loop
+ * runs when the net suspends each _search() once (mcts.py:228-242): K select_leaf()s back to back, each leaving its
+ * virtual loss behind, a terminal leaf backed up on the spot, then the K expand/backup pairs in the same order; the
+ * first wave of a search is min(K, A) wide.
+ * noise float64[n_games][A] = Dirichlet sample already multiplied by the legal mask (mcts.py:220-223) or NULL when
+ * alpha <= 0; coeff = dirichlet[1].  Unexpanded roots get the extra initial _search() (mcts.py:207-208) before the
+ * prior mix, exactly as the reference orders it.  The noise buffer must stay valid until the search has finished. */
+int dbaz_search_begin(dbaz_engine *e, const int32_t *num_reads, int32_t pending, const double *noise, double coeff,
+                      uint64_t stream);
+/* One lock-step wave = for every tree: [expand + backup of its pending leaves, in selection order, using
+ * priors/values] then [up to `pending` x (select_leaf + lazy child creation + feature gather)]
+ * (mcts.py:105-132,184-199).  All per-leaf buffers have pending * n_games rows; the row of in-flight slot k of
+ * tree t is k * n_games + t (so with pending == 1 row == tree).
+ *   priors float32[rows][A], values float32[rows]: net outputs for the leaves emitted by the PREVIOUS step
+ *   (probabilities, i.e. exp(log_softmax), and tanh value; nn.py:155-160).
+ *   planes: net input for the leaves selected by THIS step; leaf_states (may be NULL): their packed states;
+ *   leaf_kind int8[rows] (may be NULL): 1 = row holds a leaf that needs evaluation, 0 = empty row.  Terminal leaves
+ *   never appear: their simulation is completed inside the step, as in the reference where it never awaits. */
 int dbaz_search_step(dbaz_engine *e, const float *priors, const float *values, void *planes, int32_t dtype,
                      int32_t layout, dbaz_state *leaf_states, int8_t *leaf_kind, uint64_t stream);
 /* UCT_search's wall-clock limit (mcts.py:201-203,232-233): no tree starts another simulation; the

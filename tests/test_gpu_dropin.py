@@ -13,6 +13,7 @@ torch = pytest.importorskip("torch")
 
 GAMES = load("games")
 MCTS = load("mcts")
+MCTS_PENDING = load("mcts_pending")
 SELFPLAY = load("selfplay")
 
 
@@ -37,8 +38,10 @@ def fake_nn_eval(state, kind):
             np.array([(((h * 31) % 5) - 2) / 2], dtype=np.float32))
 
 
-def make_nn(kind):
+def make_nn(kind, yielding=False):
     async def nn(state):
+        if yielding:
+            await asyncio.sleep(0)
         return fake_nn_eval(state, kind)
     return nn
 
@@ -113,6 +116,42 @@ def test_uct_search_dropin(api, si):
         assert [int(ts.max_deepness), int(ts.tree_size), int(ts.terminal_count)] == ref["stats"][:3]
         assert np.float32(ts.q_value) == np.float32(ref["stats"][3])
         assert root.parent.get_tree_stats() == ts
+    BoxesState.init_static_fields(((3, 3),))
+
+
+@pytest.mark.parametrize("si", [0, 2, 4, 6])
+def test_uct_search_dropin_with_pending_evals(api, si):
+    """UCT_search(max_pending_evals=K) with a net that suspends once per call, as the reference's batching proxy does:
+    K leaves are awaited concurrently per wave and the visit counts equal the reference's."""
+    warnings.filterwarnings("ignore")
+    m, BoxesState = api["mcts"], api["BoxesState"]
+    S = MCTS_PENDING[si]
+    BoxesState.init_static_fields(((S["L"], S["C"]),))
+    s = BoxesState()
+    for mv in S["pre_moves"]:
+        s.play_(mv)
+    root = m.create_root_uct_node(s)
+    if S["seed"] is not None:
+        np.random.seed(S["seed"])
+    in_flight = {"now": 0, "max": 0}
+    base = make_nn(S["kind"], yielding=True)
+
+    async def nn(state):
+        in_flight["now"] += 1
+        in_flight["max"] = max(in_flight["max"], in_flight["now"])
+        try:
+            return await base(state)
+        finally:
+            in_flight["now"] -= 1
+    for i, st in enumerate(S["steps"][:8]):
+        if st["op"] == "search":
+            vis = asyncio.run(m.UCT_search(root, st["num_reads"], nn, cpuct=tuple(S["cpuct"]), max_pending_evals=S["max_pending"],
+                                           dirichlet=(st["alpha"], st["coeff"])))
+            assert vis.tolist() == st["root"]["visits"], (si, i)
+        else:
+            root = m.init_mcts_tree(root, st["move"], reuse_tree=st["reuse"])
+        assert np.array_equal(root.child_total_value, unhex(st["root"]["W"], np.float32))
+    assert in_flight["max"] > 1  # the caller's net really saw concurrent requests
     BoxesState.init_static_fields(((3, 3),))
 
 

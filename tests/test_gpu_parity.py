@@ -107,14 +107,15 @@ def _check_root(eng, ref, where):
 
 
 def test_mcts_sessions_vs_reference_fixtures(mods):
-    """Every recorded UCT_search / init_mcts_tree session of the reference, one tree at a time."""
+    """Every recorded UCT_search / init_mcts_tree session of the reference, one tree at a time: the sequential ones
+    (max_pending_evals = 1) and the ones with 4..64 simulations in flight."""
     engine, oracle = mods
-    MCTS = load("mcts")
+    MCTS = load("mcts") + load("mcts_pending")
     engines = {}
     for si, S in enumerate(MCTS):
         key = (S["L"], S["C"])
         if key not in engines:
-            engines[key] = engine.Engine(key, n_games=1, max_nodes=8192, cpuct=S["cpuct"])
+            engines[key] = engine.Engine(key, n_games=1, max_nodes=8192, cpuct=S["cpuct"], max_pending=64)
         eng = engines[key]
         st = eng.new_states(1)
         for m in S["pre_moves"]:
@@ -127,7 +128,8 @@ def test_mcts_sessions_vs_reference_fixtures(mods):
                 noise = None
                 if "noise" in step:
                     noise = torch.from_numpy(unhex(step["noise"], np.float64)).reshape(1, -1)
-                eng.run_search(step["num_reads"], ev, noise=noise, coeff=step["coeff"])
+                eng.run_search(step["num_reads"], ev, noise=noise, coeff=step["coeff"], pending=S.get("max_pending", 1),
+                               graph_waves=4 if si % 5 == 0 else 0)
             else:
                 eng.advance_roots([step["move"]], reuse=step["reuse"])
             _check_root(eng, step["root"], (si, i, step["op"]))
@@ -136,14 +138,15 @@ def test_mcts_sessions_vs_reference_fixtures(mods):
         e.close()
 
 
-@pytest.mark.parametrize("board,n_games,sims,kind", [((3, 3), 256, 800, 0), ((3, 3), 128, 200, 1), ((5, 5), 64, 300, 0),
-                                                     ((2, 2), 64, 100, 1), ((4, 4), 32, 150, 0)])
-def test_batched_search_vs_oracle(mods, board, n_games, sims, kind):
+@pytest.mark.parametrize("board,n_games,sims,kind,pending", [((3, 3), 256, 800, 0, 1), ((3, 3), 128, 200, 1, 1), ((5, 5), 64, 300, 0, 1),
+                                                             ((2, 2), 64, 100, 1, 1), ((4, 4), 32, 150, 0, 1),
+                                                             ((3, 3), 128, 800, 0, 8), ((3, 3), 64, 800, 1, 64), ((5, 5), 32, 300, 0, 16)])
+def test_batched_search_vs_oracle(mods, board, n_games, sims, kind, pending):
     """Many trees in lock-step from different seeded start positions, several moves with tree reuse;
     visit counts, W, priors and tree stats of every tree must equal the oracle's bit for bit."""
     engine, oracle = mods
     L, C = board
-    eng = engine.Engine(board, n_games=n_games, max_nodes=4096)
+    eng = engine.Engine(board, n_games=n_games, max_nodes=4096, max_pending=pending)
     rng = np.random.RandomState(42)
     og = [oracle.OracleGame(L, C) for _ in range(n_games)]
     st = eng.new_states(n_games)
@@ -163,7 +166,7 @@ def test_batched_search_vs_oracle(mods, board, n_games, sims, kind):
         reads = np.array([sims if g % 5 else sims // 2 for g in range(n_games)], np.int32)
         term = np.array([t.root()["is_terminal"] for t in trees])
         reads[term] = -1
-        eng.run_search(torch.from_numpy(reads), ev, max_reads=sims)
+        eng.run_search(torch.from_numpy(reads), ev, max_reads=sims, pending=pending, graph_waves=8 if move_i % 2 else 0)
         vis = eng.root_visits().cpu().numpy()
         W, P, S, U = (x.cpu().numpy() for x in eng.root_children())
         stt, rW, q = (x.cpu().numpy() for x in eng.tree_stats())
@@ -171,7 +174,7 @@ def test_batched_search_vs_oracle(mods, board, n_games, sims, kind):
         for g in range(n_games):
             if term[g]:
                 continue
-            ov = trees[g].search(int(reads[g]))
+            ov = trees[g].search(int(reads[g]), max_pending=pending)
             r = trees[g].root()
             assert np.array_equal(vis[g], ov), (move_i, g)
             assert np.array_equal(W[g], r["W"]) and np.array_equal(P[g], r["priors"]), (move_i, g)
