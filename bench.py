@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--net-plan", default="fused", choices=["fused", "module"],
                     help="fused: library convs/GEMMs + the engine's fused epilogue kernels; module: the plain nn.Module")
     ap.add_argument("--graph-waves", type=int, default=16)
+    ap.add_argument("--pending", type=int, default=1,
+                    help="max_pending_evals: simulations in flight per tree (1 = strictly sequential, BASELINE configs[1]; "
+                         "the reference ships 64, configuration.py:35)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="processes for the CPU baseline (0 = min(cores-1, 64))")
     ap.add_argument("--cpu-positions", type=int, default=2, help="searches per worker in the bounded CPU sample")
@@ -220,7 +223,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     L, C = (int(x) for x in args.board.split("x"))
-    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.sims + 8, device=dev)
+    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.sims + 8, device=dev, max_pending=args.pending)
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.net_dtype]
     if args.net == "fake":
         ev = engine.FakeNetEvaluator(0)
@@ -241,7 +244,7 @@ def main():
 
     def step_resident():
         eng.reset_roots(roots)
-        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves)
+        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves, pending=args.pending)
         visits.copy_(eng.root_visits())
 
     # host buffers of the end-to-end arm (pinned)
@@ -255,7 +258,7 @@ def main():
         roots_in.copy_(roots_host, non_blocking=True)
         noise_dev.copy_(noise_host, non_blocking=True)
         eng.reset_roots(roots_in)
-        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves)
+        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves, pending=args.pending)
         visits_host.copy_(eng.root_visits(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return int(visits_host[0].sum())
@@ -307,13 +310,14 @@ def main():
     roof = None
     if rank == 0:
         eng.reset_roots(roots)
-        eng.begin(args.sims, noise_dev, NOISE[1])
+        eng.begin(args.sims, noise_dev, NOISE[1], pending=args.pending)
         evs = []
-        for w in range(args.sims + 1):
+        n_waves = 2 + max(0, -(-(args.sims - min(args.pending, eng.A)) // args.pending))
+        for w in range(n_waves):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); eng.step(); b.record()
             ev(eng)
-            if 16 <= w < args.sims:
+            if min(16, n_waves // 4) <= w < n_waves - 1:
                 evs.append((a, b))
         eng.step()
         torch.cuda.synchronize()
@@ -324,7 +328,8 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = bytes_per_sim * args.games / (k_ms * 1e-3) / 1e9
+        sims_per_launch = args.games * args.sims / max(1, n_waves - 2)  # simulations one launch processes on average
+        achieved = bytes_per_sim * sims_per_launch / (k_ms * 1e-3) / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_search_step_dram_bytes_per_launch")
@@ -333,7 +338,8 @@ def main():
         roof = {"bound": "hbm", "kernel": "k_search_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "kernel_us": k_ms * 1e3, "algorithmic_bytes_per_sim": bytes_per_sim, "mean_path_nodes": P,
-                "terminal_leaf_frac": f_term, "share_of_step": k_ms * (args.sims + 2) / (ms / args.steps)}
+                "terminal_leaf_frac": f_term, "share_of_step": k_ms * n_waves / (ms / args.steps),
+                "sims_per_launch": sims_per_launch}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -341,7 +347,7 @@ def main():
                 "dtype": "f64 PUCT over f32/i32 node stats; net %s" % (args.net_dtype if args.net != "fake" else "none (fake)"),
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "board": args.board, "games_per_gpu": args.games,
-                           "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "net_plan": args.net_plan, "parallelism": "games sharded by index x%d, no collective" % world,
+                           "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "net_plan": args.net_plan, "max_pending_evals": args.pending, "parallelism": "games sharded by index x%d, no collective" % world,
                            "l2": "inputs larger than L2: node pool touched per step %.2f GB/GPU vs 126 MB L2" % (
                                args.games * (args.sims + 1) * eng.node_bytes / 1e9),
                            "graph_waves": args.graph_waves},
