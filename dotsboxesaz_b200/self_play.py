@@ -338,6 +338,101 @@ class BatchedSelfPlay:
                                       [vis[m, g] for m in range(act.shape[0]) if act[m, g]], z))
 
 
+class DualEvaluator:
+    """Two nets, one per player, for the Elo arena (self_play.py:237-239 swaps the model on every move according to
+    the player to move at the ROOT): both nets evaluate the wave and each game keeps the rows of the model that owns
+    its current root.  `owner` (int8 [n_games], 0/1) is set by the driver before every search."""
+
+    def __init__(self, ev0, ev1, engine):
+        self.evs = (ev0, ev1)
+        self.owner = torch.zeros((engine.n_games,), dtype=torch.bool, device=engine.device)
+        self.engine_launches = getattr(ev0, "engine_launches", 0) + getattr(ev1, "engine_launches", 0)
+        self._p0 = torch.empty_like(engine._priors)
+        self._v0 = torch.empty_like(engine._values)
+
+    def __call__(self, eng):
+        rows = eng.n_rows
+        self.evs[0](eng)
+        self._p0[:rows].copy_(eng.priors)
+        self._v0[:rows].copy_(eng.values)
+        self.evs[1](eng)
+        own1 = self.owner.repeat(eng.pending)  # row of slot k of tree t = k * n_games + t
+        eng.priors.copy_(torch.where(own1.unsqueeze(1), eng.priors, self._p0[:rows]))
+        eng.values.copy_(torch.where(own1, eng.values, self._v0[:rows]))
+
+
+def compute_elo(elo_params, params, generations, elos, models=None, engine=None):
+    """self_play.py:309-344: `elo_params.n_games` games between the nets of two generations (no tree reuse, no noise,
+    more reads: elo_params.self_play_override), colours alternated between games, ratings updated with elo_rating2.
+    models: the two nn.Modules (else built from params[i].nn.model_class and loaded from their checkpoints).
+    Returns (elo0, elo1, share of games won by generations[1])."""
+    import copy
+    from . import engine as _engine
+    from .nn import make_evaluator
+    from .utils.utils import elo_rating2
+    params = [copy.deepcopy(p) for p in params]
+    for p in params:
+        p.self_play.merge(elo_params.self_play_override)
+    n = int(elo_params.n_games)
+    if engine is None:
+        engine = _engine.Engine(tuple(params[0].game.clazz.BOARD_DIM), n_games=n,
+                                max_nodes=int(params[0].self_play.get("max_nodes_per_tree", 8192) or 8192))
+    if models is None:
+        models = []
+        for p, g in zip(params, generations):
+            m = p.nn.model_class(p)
+            if g != 0:
+                m.load_parameters(g, to_device=engine.device)
+            models.append(m)
+    dual = DualEvaluator(make_evaluator(models[0], engine), make_evaluator(models[1], engine), engine)
+    sp = BatchedSelfPlay(engine, dual, params[0], pending=1)
+    # player p of game g is generation (p + g) % 2: colours alternate between games (the reference shuffles by worker pid)
+    swap = torch.arange(n, device=engine.device) % 2 == 1
+    eng = engine
+    eng.set_cpuct(params[0].self_play.mcts.mcts_cpuct)
+    eng.reset_roots()
+    alpha, coeff = params[0].self_play.noise
+    temperature, move_i = None, -1
+    gen = torch.Generator(device=eng.device)
+    gen.manual_seed(int(elo_params.get("seed", 0) or 0))
+    n_edges = eng.L * (eng.C + 1) + eng.C * (eng.L + 1)
+    for move_i in range(n_edges):
+        if move_i in params[0].self_play.mcts.temperature:
+            temperature = float(params[0].self_play.mcts.temperature[move_i])
+        roots = eng.root_states()
+        active = eng.result(roots) == RESULT_NONE
+        if not bool(active.any()):
+            break
+        to_play = roots.view(torch.uint8).reshape(n, 32)[:, 20].bool()
+        dual.owner.copy_(to_play ^ swap)
+        k = n_edges - move_i
+        reads = torch.where(active, torch.full((n,), _n_searches(k, params[0].self_play.mcts.mcts_num_read), dtype=torch.int32,
+                                               device=eng.device), torch.full((n,), -1, dtype=torch.int32, device=eng.device))
+        noise = None
+        if alpha > 0:
+            g_ = torch._standard_gamma(torch.full((n, eng.A), float(alpha), dtype=torch.float64, device=eng.device), generator=gen)
+            noise = g_ / g_.sum(-1, keepdim=True) * eng.valid_moves(roots)
+        eng.run_search(reads, dual, noise=noise, coeff=coeff, max_reads=_n_searches(k, params[0].self_play.mcts.mcts_num_read))
+        v = eng.root_visits().double()
+        probs = (v / v.max(1, keepdim=True).values.clamp_min(1.0)) ** (1.0 / temperature)
+        probs = torch.where(active.unsqueeze(1), probs, eng.valid_moves(roots).double())
+        probs = probs + (probs.sum(1, keepdim=True) == 0).double()
+        moves = torch.multinomial(probs, 1, generator=gen).reshape(-1).int()
+        eng.advance_roots(torch.where(active, moves, torch.full_like(moves, -1)), reuse=bool(params[0].self_play.reuse_mcts_tree))
+    final = eng.root_states()
+    res = eng.result(final)
+    eng.status()
+    winner_player = final.view(torch.uint8).reshape(n, 32)[:, 21].bool()  # just_played of the terminal state
+    decided = res != 0
+    winner_gen = (winner_player ^ swap) & decided
+    n1 = int(winner_gen.sum())
+    n0 = int(decided.sum()) - n1
+    elo0, elo1 = elo_rating2(elos[0], elos[1], n0, n1, K=30)
+    print(f"generation {generations[0]}: wins={n0}, elo={elos[0]} -> {elo0}")
+    print(f"generation {generations[1]}: wins={n1}, elo={elos[1]} -> {elo1}")
+    return elo0, elo1, n1 / max(1, n0 + n1)
+
+
 def shard_game_indices(n_games, rank, world):
     """Games are independent: rank r plays the indices i with i % world == r (self_play.py:184 does the
     same round-robin over devices with its worker pids)."""

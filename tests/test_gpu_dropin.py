@@ -239,3 +239,43 @@ def test_device_resident_selfplay_is_valid_play(api):
             og.play_(int(moves[m, g]))
         assert og.result() == int(res[g])
     eng.close()
+
+
+def test_batching_proxy_in_front_of_a_torch_net(api):
+    """The reference's stack: UCT_search(max_pending_evals=K) -> AsyncBatchedProxy -> NeuralNetWrapper(model).  The
+    proxy must see real batches because the drop-in awaits its K leaves concurrently."""
+    warnings.filterwarnings("ignore")
+    from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
+    from dotsboxesaz_b200.nn import NeuralNetWrapper
+    from dotsboxesaz_b200.utils.proxies import AsyncBatchedProxy
+    m, BoxesState, DotDict = api["mcts"], api["BoxesState"], api["DotDict"]
+    BoxesState.init_static_fields(((3, 3),))
+    torch.manual_seed(0)
+    wrapper = NeuralNetWrapper(SimpleNN(board=(3, 3)), DotDict({"nn": {"pytorch_device": "cuda:0"}}))
+
+    async def main():
+        proxy = AsyncBatchedProxy(wrapper, batch_size=16, timeout=0.01, batch_builder=api["nn_batch_builder"], cache_size=1000)
+        task = asyncio.ensure_future(proxy.run())
+        root = m.create_root_uct_node(BoxesState())
+        vis = await m.UCT_search(root, 96, proxy, max_pending_evals=16, dirichlet=(0.0, 0.0))
+        task.cancel()
+        return vis, proxy
+    vis, proxy = asyncio.run(main())
+    assert int(vis.sum()) == 96
+    assert proxy.n_batches < proxy.n_evals  # batches of more than one leaf were dispatched
+
+
+def test_elo_arena_identical_nets_split_wins(api):
+    """compute_elo with the same weights on both sides: every game is decided, colours alternate, and both ratings
+    move by equal and opposite amounts."""
+    from dotsboxesaz_b200 import configuration
+    from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
+    api["BoxesState"].init_static_fields(((3, 3),))
+    params = configuration.simple
+    elo = api["DotDict"]({"n_games": 64, "seed": 3, "self_play_override": {"reuse_mcts_tree": False, "noise": (0.0, 0.0),
+                                                                          "mcts": {"mcts_num_read": 40}}})
+    torch.manual_seed(1)
+    net = SimpleNN(board=(3, 3))
+    e0, e1, share = api["self_play"].compute_elo(elo, [params, params], [1, 2], (1200, 1200), models=[net, net])
+    assert abs((e0 - 1200) + (e1 - 1200)) < 1e-9
+    assert 0.0 <= share <= 1.0

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--max-nodes", type=int, default=8192)
     ap.add_argument("--mode", default="device", choices=["device", "host"])
     ap.add_argument("--repeats", type=int, default=1)
+    ap.add_argument("--pending", type=int, default=1, help="max_async_searches (simulations in flight per tree)")
+    ap.add_argument("--no-warmup", action="store_true")
     args = ap.parse_args()
     import torch
     from dotsboxesaz_b200 import engine, self_play
@@ -28,7 +30,7 @@ def main():
     from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
     from dotsboxesaz_b200.utils.utils import DotDict
     L, C = (int(x) for x in args.board.split("x"))
-    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.max_nodes)
+    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.max_nodes, max_pending=args.pending)
     torch.manual_seed(0)
     if args.net == "fake":
         ev = engine.FakeNetEvaluator(0)
@@ -38,7 +40,7 @@ def main():
         ev = FusedResNetZero(ResNetZero(DotDict({"nn": {"model_parameters": resnet_zero_parameters((L, C))}})), eng)
     params = DotDict({"self_play": {"reuse_mcts_tree": True, "noise": (0.8, 0.25),
                                     "mcts": {"mcts_num_read": args.sims, "mcts_cpuct": (1.25, 19652),
-                                             "temperature": {0: 1.0, 12: 0.02}, "max_async_searches": 1}}})
+                                             "temperature": {0: 1.0, 12: 0.02}, "max_async_searches": args.pending}}})
     for rep in range(args.repeats + 1):  # first pass warms up (graphs, cuDNN)
         sp = self_play.BatchedSelfPlay(eng, ev, params, graph_waves=16)
         torch.cuda.synchronize()
@@ -52,9 +54,9 @@ def main():
             rows = len(sp.rows)
         torch.cuda.synchronize()
         dt = time.time() - t0
-        if rep == 0:
+        if rep == 0 and not args.no_warmup:
             continue
-        print(json.dumps({"board": args.board, "games": args.games, "sims_per_move": args.sims, "net": args.net, "mode": args.mode,
+        print(json.dumps({"board": args.board, "games": args.games, "sims_per_move": args.sims, "net": args.net, "mode": args.mode, "max_pending_evals": args.pending,
                           "seconds": dt, "games_per_hour": args.games / dt * 3600, "sims_per_sec": info["sims"] / dt,
                           "total_sims": info["sims"], "sample_rows": rows, "max_nodes_used": info["max_nodes_used"],
                           "mean_path_nodes": info["path_nodes"] / max(1, info["sims"]),
