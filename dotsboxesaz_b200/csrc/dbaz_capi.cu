@@ -59,10 +59,13 @@ inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
 int upload_lut(dbaz_engine* e) {
     // c0(N) = log((N + base + 1) / base) + cpuct with the host libm -- the same function CPython's
     // math.log calls (mcts.py:92-93) -- so no device log ulp difference can flip an argmax.
-    std::vector<double> lut(e->ta.lut_size);
-    for (int n = 0; n < e->ta.lut_size; ++n)
-        lut[n] = std::log(((double)n + e->ta.cpuct_base + 1.0) / e->ta.cpuct_base) + e->ta.cpuct;
-    DBAZ_CK(e, cudaMemcpy(const_cast<double*>(e->ta.lut), lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // sqrt(N) rides along in the same 16-byte entry (IEEE sqrt is correctly rounded on both sides).
+    std::vector<double2> lut(e->ta.lut_size);
+    for (int n = 0; n < e->ta.lut_size; ++n) {
+        lut[n].x = std::log(((double)n + e->ta.cpuct_base + 1.0) / e->ta.cpuct_base) + e->ta.cpuct;
+        lut[n].y = std::sqrt((double)n);
+    }
+    DBAZ_CK(e, cudaMemcpy(const_cast<double2*>(e->ta.lut), lut.data(), lut.size() * sizeof(double2), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -175,7 +178,7 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
               alloc((void**)&ta.trees, (size_t)ta.n_trees * sizeof(TreeRec), "tree table") &&
               alloc((void**)&ta.root_prior, (size_t)ta.n_trees * A * sizeof(double), "root priors") &&
               alloc((void**)&ta.path, (size_t)max_pending * ta.n_trees * PATH_CAP * sizeof(uint32_t), "paths") &&
-              alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double), "log table") &&
+              alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double2), "log/sqrt table") &&
               alloc((void**)&ta.act_tab, (size_t)A * 2 * sizeof(uint4), "action table") &&
               alloc((void**)&ta.pend, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4), "pending leaves") &&
               alloc((void**)&e->d_status, 8 * sizeof(unsigned long long), "status");
@@ -206,7 +209,7 @@ void dbaz_engine_destroy(dbaz_engine* e) {
     cudaFree(e->ta.trees);
     cudaFree(e->ta.root_prior);
     cudaFree(e->ta.path);
-    cudaFree(const_cast<double*>(e->ta.lut));
+    cudaFree(const_cast<double2*>(e->ta.lut));
     cudaFree(const_cast<uint4*>(e->ta.act_tab));
     cudaFree(e->ta.pend);
     cudaFree(e->d_status);

@@ -81,7 +81,7 @@ struct TreeArgs {
     TreeRec* trees;
     double* root_prior;   // [n_trees][A]
     uint32_t* path;       // [n_trees][PATH_CAP]
-    const double* lut;    // c0(N) = log((N + base + 1)/base) + cpuct, host libm
+    const double2* lut;   // {c0(N) = log((N + base + 1)/base) + cpuct, sqrt(N)}, host libm
     const uint4* act_tab; // [A][2]: the two box masks each action borders (built once per engine)
     uint4* pend;          // [max_pending][n_trees][3]: pending leaf {header copy (2 x 16 B), node index, path length}
     int max_pending;      // lanes of in-flight simulations per tree; row of lane k of tree t = k * n_trees + t
@@ -161,10 +161,16 @@ __device__ __forceinline__ Mask<NW> hdr_edges(const Hdr& h) {
     return m;
 }
 
-__device__ __forceinline__ double puct_c0(const TreeArgs& ta, int N) {
+// {c0(N), sqrt(N)} of mcts.py:92-94 for a node with N own visits: one 16-byte load from a table the host built with
+// libm (the functions CPython's math.log / math.sqrt call), issued together with the node's loads, instead of a
+// float64 log + sqrt instruction chain behind them.
+__device__ __forceinline__ double2 puct_consts(const TreeArgs& ta, int N) {
     if (N < ta.lut_size) return ta.lut[N];
-    // beyond the host table: device log (<= 1 ulp from libm; documented in DESIGN.md)
-    return __dadd_rn(log(__ddiv_rn(__dadd_rn(__dadd_rn((double)N, ta.cpuct_base), 1.0), ta.cpuct_base)), ta.cpuct);
+    // beyond the host table: device log (<= 1 ulp from libm; documented in DESIGN.md), IEEE sqrt
+    double2 r;
+    r.x = __dadd_rn(log(__ddiv_rn(__dadd_rn(__dadd_rn((double)N, ta.cpuct_base), 1.0), ta.cpuct_base)), ta.cpuct);
+    r.y = __dsqrt_rn((double)N);
+    return r;
 }
 
 // Per-lane constants of the lane -> action mapping (action = lane + 32*k): own bit and the two
@@ -429,10 +435,11 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
     int cur = 0, curN = T.root_N, depth = 0;
     int leaf = -1;
     Hdr leaf_hdr;
+    char* const tree_base = node_ptr(ta, t, 0);
     float* vl_cell = nullptr;  // W of the current node's own record (valid on the lane that owned the action)
     float vl_w = 0.0f;
     while (true) {
-        char* np = node_ptr(ta, t, cur);
+        char* np = tree_base + (size_t)cur * (size_t)ta.stride;
         // header and child records are fetched together; an unexpanded / terminal node has garbage
         // child records, which are loaded but never interpreted
         const uint4* hp = reinterpret_cast<const uint4*>(np);
@@ -444,7 +451,7 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
             craw[k] = make_uint4(0, 0, 0, 0);
             if (a < A) craw[k] = hp[2 + a];
         }
-        const double c0 = puct_c0(ta, curN);
+        const double2 cs = puct_consts(ta, curN);
         double rprior[APL];
         if (depth == 0) {
 #pragma unroll
@@ -459,17 +466,20 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
         else if (vl_cell) *vl_cell = __fsub_rn(vl_w, 1.0f);
 
         const Mask<NW> e = hdr_edges<NW>(h);
-        const double sq = __dsqrt_rn((double)curN);
+        const double c0 = cs.x, sq = cs.y;
         double best = -INFINITY;
         int best_a = 0x7fffffff;
+        int ncl_k[APL];  // boxes each of this lane's actions would close (decides the child's sign and who moves next)
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
             const int a = lane + 32 * k;
             const bool legal = la.real[k] && !mask_test(e, a < A ? a : 0);
+            ncl_k[k] = 0;
             if (legal) {
                 Child c;
                 c.W = __uint_as_float(craw[k].x); c.N = (int)craw[k].y; c.prior = __uint_as_float(craw[k].z);
-                const int sign = la.closes(k, e, a) ? 1 : -1;
+                ncl_k[k] = la.closes(k, e, a);
+                const int sign = ncl_k[k] ? 1 : -1;
                 const double prior = (depth == 0) ? rprior[k] : (double)c.prior;
                 const double sc = ucb_score<APL, NW>(c0, sq, c, prior, sign);
                 if (best_a == 0x7fffffff || sc > best) { best = sc; best_a = a; }
@@ -482,7 +492,7 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
 #pragma unroll
         for (int k = 0; k < APL; ++k)
             if (k == kk) {
-                child = (int)craw[k].w; childN = (int)craw[k].y; ncl = la.closes(k, e, lane + 32 * k);
+                child = (int)craw[k].w; childN = (int)craw[k].y; ncl = ncl_k[k];
                 if (lane == owner) { vl_cell = &node_children(np)[a].W; vl_w = __uint_as_float(craw[k].x); }
             }
         child = __shfl_sync(0xffffffffu, child, owner);
@@ -823,7 +833,8 @@ __global__ void k_root_children(Board b, TreeArgs ta, float* __restrict__ W, dou
     bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
     const Child* ch = node_children(np);
     Mask<NW> e = load_edges<NW>(h);
-    double c0 = puct_c0(ta, T.root_N), sq = __dsqrt_rn((double)T.root_N);
+    const double2 cs = puct_consts(ta, T.root_N);
+    double c0 = cs.x, sq = cs.y;
     for (int a = lane; a < A; a += 32) {
         Child c; c.W = 0.0f; c.N = 0; c.prior = 0.0f; c.child = 0;
         if (interior) c = ch[a];
