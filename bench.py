@@ -46,6 +46,12 @@ def parse_args():
     ap.add_argument("--pending", type=int, default=1,
                     help="max_pending_evals: simulations in flight per tree (1 = strictly sequential, BASELINE configs[1]; "
                          "the reference ships 64, configuration.py:35)")
+    ap.add_argument("--eval-cache", type=int, default=22,
+                    help="log2(entries) of the device eval cache (the reference's LRU of net outputs, utils/proxies.py:23-26); "
+                         "emptied at the start of EVERY step, inside the timed region; 0 = off")
+    ap.add_argument("--no-adaptive", action="store_true", help="fixed number of full-width waves instead of the adaptive loop")
+    ap.add_argument("--max-inline", type=int, default=4, help="bound on simulations per tree and wave finished without the net")
+    ap.add_argument("--no-ablation", action="store_true", help="skip the extra no-cache measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="processes for the CPU baseline (0 = min(cores-1, 64))")
     ap.add_argument("--cpu-positions", type=int, default=2, help="searches per worker in the bounded CPU sample")
@@ -223,7 +229,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     L, C = (int(x) for x in args.board.split("x"))
-    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.sims + 8, device=dev, max_pending=args.pending)
+    use_cache = args.eval_cache if args.pending == 1 else 0
+    adaptive = (not args.no_adaptive) and args.pending == 1 and args.graph_waves > 0
+    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.sims + 8, device=dev, max_pending=args.pending,
+                        eval_cache=use_cache)
+    eng.set_mode(False, args.max_inline)
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.net_dtype]
     if args.net == "fake":
         ev = engine.FakeNetEvaluator(0)
@@ -242,9 +252,14 @@ def main():
     noise_dev = torch.from_numpy(host_noise(rs, valid_np, NOISE[0])).to(dev)
     visits = torch.empty((args.games, eng.A), dtype=torch.int32, device=dev)
 
+    def search():
+        eng.clear_eval_cache()  # every step starts with an empty table: only reuse within the step's own searches counts
+        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves, pending=args.pending,
+                       adaptive=adaptive)
+
     def step_resident():
         eng.reset_roots(roots)
-        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves, pending=args.pending)
+        search()
         visits.copy_(eng.root_visits())
 
     # host buffers of the end-to-end arm (pinned)
@@ -258,7 +273,7 @@ def main():
         roots_in.copy_(roots_host, non_blocking=True)
         noise_dev.copy_(noise_host, non_blocking=True)
         eng.reset_roots(roots_in)
-        eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves, pending=args.pending)
+        search()
         visits_host.copy_(eng.root_visits(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return int(visits_host[0].sum())
@@ -287,9 +302,10 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = eng.n_launches
+    l0, w0 = eng.n_launches, eng.n_waves
     ms, _wall = timed(step_resident, args.steps)
     launches = eng.n_launches - l0
+    waves_per_step = (eng.n_waves - w0) / args.steps
     st = eng.status()  # also checks that no tree faulted
     for _ in range(2):
         step_e2e()
@@ -304,23 +320,37 @@ def main():
     # the launching stream, one event pair per launch, with the real evaluator between launches
     P = st["path_nodes"] / max(1, st["sims"])
     f_term = st["terminal_leaves"] / max(1, st["sims"])
+    f_hit = st["cache_hits"] / max(1, st["sims"])
+    f_miss = 1.0 - f_term - f_hit  # simulations whose leaf the net evaluated
     A, F = eng.A, eng.F
     plane_b = 4 if (args.net == "fake" or args.net_dtype == "fp32") else 2
-    bytes_per_sim = (P - 1) * (13 * A + 24) + 36 + 24 * P + (1 - f_term) * (F * plane_b + 17 * A + 4)
+    # select + leaf create + backup | expand (node priors out, zeroed stats, value) |
+    # features out + net priors in (evaluated leaves only) | eval cache probe (every non-terminal leaf) + insert
+    bytes_per_sim = ((P - 1) * (13 * A + 24) + 36 + 24 * P + (1 - f_term) * (13 * A + 4) + f_miss * (F * plane_b + 4 * A)
+                     + ((1 - f_term) * 16 * A + f_miss * 16 * A if use_cache else 0))
     roof = None
+    ablation = None
     if rank == 0:
         eng.reset_roots(roots)
+        eng.clear_eval_cache()
+        eng.set_mode(adaptive, args.max_inline)
         eng.begin(args.sims, noise_dev, NOISE[1], pending=args.pending)
         evs = []
         n_waves = 2 + max(0, -(-(args.sims - min(args.pending, eng.A)) // args.pending))
-        for w in range(n_waves):
+        s0 = eng.status()["sims"]
+        w = 0
+        while w < n_waves:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); eng.step(); b.record()
             ev(eng)
-            if min(16, n_waves // 4) <= w < n_waves - 1:
-                evs.append((a, b))
+            evs.append((a, b))
+            w += 1
+            if adaptive and w % 8 == 0 and eng.wave_counts()[1] == 0:
+                break
         eng.step()
         torch.cuda.synchronize()
+        n_run = len(evs)
+        evs = evs[min(16, n_run // 4):]
         k_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
         peaks = {}
         try:
@@ -328,7 +358,7 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        sims_per_launch = args.games * args.sims / max(1, n_waves - 2)  # simulations one launch processes on average
+        sims_per_launch = (eng.status()["sims"] - s0) / n_run  # simulations one launch processes on average
         achieved = bytes_per_sim * sims_per_launch / (k_ms * 1e-3) / 1e9
         traffic = None
         try:
@@ -338,8 +368,22 @@ def main():
         roof = {"bound": "hbm", "kernel": "k_search_step", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "kernel_us": k_ms * 1e3, "algorithmic_bytes_per_sim": bytes_per_sim, "mean_path_nodes": P,
-                "terminal_leaf_frac": f_term, "share_of_step": k_ms * n_waves / (ms / args.steps),
-                "sims_per_launch": sims_per_launch}
+                "terminal_leaf_frac": f_term, "cache_hit_frac": f_hit, "share_of_step": k_ms * waves_per_step / (ms / args.steps),
+                "sims_per_launch": sims_per_launch, "launches_per_step": waves_per_step}
+        if use_cache and not args.no_ablation and world == 1:
+            # the same step with the table switched off (fixed wave loop, row == tree): what the cache buys
+            eng.set_eval_cache(0)
+
+            def step_plain():
+                eng.reset_roots(roots)
+                eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves, pending=args.pending)
+                visits.copy_(eng.root_visits())
+            ref_visits = visits.clone()
+            step_plain()
+            same = bool((ref_visits == visits).all())
+            ms_plain, _ = timed(step_plain, 2)
+            ablation = {"no_eval_cache_sims_per_sec": args.games * args.sims * 2 / (ms_plain / 1e3),
+                        "visit_counts_equal_to_cached_run": same}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -347,7 +391,9 @@ def main():
                 "dtype": "f64 PUCT over f32/i32 node stats; net %s" % (args.net_dtype if args.net != "fake" else "none (fake)"),
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "board": args.board, "games_per_gpu": args.games,
-                           "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "net_plan": args.net_plan, "max_pending_evals": args.pending, "parallelism": "games sharded by index x%d, no collective" % world,
+                           "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "net_plan": args.net_plan, "max_pending_evals": args.pending,
+                           "eval_cache": ("2^%d entries, emptied at the start of every step" % use_cache) if use_cache else "off",
+                           "wave_loop": "adaptive (compact rows, batch ladder)" if adaptive else "fixed", "parallelism": "games sharded by index x%d, no collective" % world,
                            "l2": "inputs larger than L2: node pool touched per step %.2f GB/GPU vs 126 MB L2" % (
                                args.games * (args.sims + 1) * eng.node_bytes / 1e9),
                            "graph_waves": args.graph_waves},
@@ -356,7 +402,7 @@ def main():
                         "h2d_bytes_per_step": int(roots_host.numel() * 8 + noise_host.numel() * 8),
                         "d2h_bytes_per_step": int(visits_host.numel() * 4),
                         "api": "Engine.reset_roots(host roots) + Engine.run_search(host Dirichlet noise) + root_visits -> host"},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ablation": ablation}
         if c_rate is not None:
             line["cpu_c_oracle_1core_sims_per_sec"] = c_rate
         print(json.dumps(line), flush=True)

@@ -50,6 +50,10 @@ SYMBOLS = {
     "dbaz_search_root_states": (C.c_int, [_P, _P, _U64]),
     "dbaz_search_advance_roots": (C.c_int, [_P, _P, _I32, _U64]),
     "dbaz_search_status": (C.c_int, [_P, _P, _U64]),
+    "dbaz_search_set_mode": (C.c_int, [_P, _I32, _I32]),
+    "dbaz_search_wave_counts": (C.c_int, [_P, _P, _U64]),
+    "dbaz_cache_configure": (C.c_int, [_P, _I32]),
+    "dbaz_cache_clear": (C.c_int, [_P, _U64]),
     "dbaz_nn_epilogue": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _U64]),
     "dbaz_nn_stem": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I64, _U64]),
     "dbaz_nn_heads": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _I64, _U64]),

@@ -25,6 +25,7 @@ struct dbaz_engine {
     const double* noise;  // caller-owned device buffer of the current search (may be null)
     double coeff;
     int pending;          // max_pending_evals of the current search
+    int cache_log2;       // log2(entries) of the eval cache, 0 = none
     unsigned long long* d_status;
     std::string err;
 };
@@ -181,6 +182,7 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
               alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double2), "log/sqrt table") &&
               alloc((void**)&ta.act_tab, (size_t)A * 2 * sizeof(uint4), "action table") &&
               alloc((void**)&ta.pend, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4), "pending leaves") &&
+              alloc((void**)&ta.ctr, 8 * sizeof(int), "wave counters") &&
               alloc((void**)&e->d_status, 8 * sizeof(unsigned long long), "status");
     if (!ok) { dbaz_engine_destroy(e); return 1; }
     if (upload_lut(e)) { g_create_err = e->err; dbaz_engine_destroy(e); return 1; }
@@ -194,6 +196,8 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     }
     k_build_act_tab<<<1, DBAZ_MAX_ACTIONS>>>(b, const_cast<uint4*>(ta.act_tab));
     cudaMemset(ta.pend, 0, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4));
+    cudaMemset(ta.ctr, 0, 8 * sizeof(int));
+    ta.cache_vcell = C;  // action C = horizontal edge (row 0, column C): always a padding cell
     cudaMemset(ta.path, 0, (size_t)max_pending * ta.n_trees * PATH_CAP * sizeof(uint32_t));
     // an all-empty-board root set so that the engine is usable right after create
     k_reset_roots<<<blocks_for(ta.n_trees, 128), 128>>>(b, ta, nullptr);
@@ -212,6 +216,8 @@ void dbaz_engine_destroy(dbaz_engine* e) {
     cudaFree(const_cast<double2*>(e->ta.lut));
     cudaFree(const_cast<uint4*>(e->ta.act_tab));
     cudaFree(e->ta.pend);
+    cudaFree(e->ta.ctr);
+    cudaFree(e->ta.cache);
     cudaFree(e->d_status);
     delete e;
 }
@@ -444,6 +450,53 @@ int dbaz_search_advance_roots(dbaz_engine* e, const int32_t* moves, int32_t reus
     else k_advance_roots<2><<<e->ta.n_trees, ADV_THREADS, e->adv_smem, S(stream)>>>(e->board, e->ta, moves, reuse);
     e->noise = nullptr; e->coeff = 0.0;
     return launch_ok(e, "k_advance_roots");
+}
+
+int dbaz_search_set_mode(dbaz_engine* e, int32_t compact, int32_t max_inline) {
+    if (!e) return 1;
+    if (max_inline < 0) return fail(e, "max_inline must be >= 0");
+    e->ta.compact = compact ? 1 : 0;
+    e->ta.max_inline = max_inline;
+    return 0;
+}
+
+int dbaz_search_wave_counts(dbaz_engine* e, int32_t* out2, uint64_t stream) {
+    if (!e || !out2) return 1;
+    DeviceGuard guard(e->cfg.device);
+    DBAZ_CK(e, cudaMemcpyAsync(out2, e->ta.ctr + 4, 2 * sizeof(int), cudaMemcpyDefault, S(stream)));
+    return 0;
+}
+
+int dbaz_cache_configure(dbaz_engine* e, int32_t log2_entries) {
+    if (!e) return 1;
+    if (log2_entries < 0 || log2_entries > 30) return fail(e, "log2_entries must be in [0, 30]");
+    if (log2_entries > 0 && e->board.A > 88) return fail(e, "the eval cache supports boards with at most 88 actions");
+    DeviceGuard guard(e->cfg.device);
+    DBAZ_CK(e, cudaDeviceSynchronize());
+    if (e->ta.cache) { cudaFree(e->ta.cache); e->ta.cache = nullptr; }
+    e->ta.cache_mask = 0; e->cache_log2 = 0;
+    if (log2_entries == 0) return 0;
+    const size_t bytes = ((size_t)1 << log2_entries) * (size_t)e->board.A * sizeof(uint4);
+    cudaError_t st = cudaMalloc((void**)&e->ta.cache, bytes);
+    if (st != cudaSuccess) {
+        e->ta.cache = nullptr;
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "cudaMalloc(eval cache, %zu bytes): %s", bytes, cudaGetErrorString(st));
+        return fail(e, buf);
+    }
+    e->ta.cache_mask = (uint32_t)(((size_t)1 << log2_entries) - 1);
+    e->cache_log2 = log2_entries;
+    DBAZ_CK(e, cudaMemset(e->ta.cache, 0xff, bytes));  // all-ones edges never occur (padding bits stay clear)
+    return 0;
+}
+
+int dbaz_cache_clear(dbaz_engine* e, uint64_t stream) {
+    if (!e) return 1;
+    if (!e->ta.cache) return 0;
+    DeviceGuard guard(e->cfg.device);
+    const size_t bytes = ((size_t)e->ta.cache_mask + 1) * (size_t)e->board.A * sizeof(uint4);
+    DBAZ_CK(e, cudaMemsetAsync(e->ta.cache, 0xff, bytes, S(stream)));
+    return 0;
 }
 
 int dbaz_search_status(dbaz_engine* e, int64_t* out8, uint64_t stream) {

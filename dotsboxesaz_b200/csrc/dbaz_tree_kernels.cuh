@@ -41,14 +41,16 @@ struct __align__(64) TreeRec {
     float root_W;         // TreeRoot.child_total_value[None] (float32 in effect)
     int32_t sims_left;
     int32_t n_pending;    // simulations selected and waiting for their evaluation (<= max_pending)
-    int32_t reserved_;
+    int32_t row;          // compact mode: row of the evaluator's batch that holds this tree's pending leaf
     uint32_t flags;
     int32_t max_deepness;
     int32_t deepness_correction;
     int32_t terminal_count;
     int32_t tree_size;
     int32_t total_term;   // terminal leaves since reset (instrumentation)
-    unsigned long long total_sims, total_path;
+    uint32_t total_sims;  // simulations since reset (instrumentation)
+    uint32_t cache_hits;  // ... of which the evaluation came out of the eval cache
+    unsigned long long total_path;
 };
 static_assert(sizeof(TreeRec) == 64, "TreeRec must be 64 bytes");
 
@@ -56,7 +58,7 @@ static_assert(sizeof(TreeRec) == 64, "TreeRec must be 64 bytes");
 struct TreeHot {
     int32_t n_nodes, root_N;
     float root_W;
-    int32_t sims_left, n_pending;
+    int32_t sims_left, n_pending, row;
     uint32_t flags;
 };
 __device__ __forceinline__ TreeHot load_hot(const TreeRec* G) {
@@ -64,12 +66,12 @@ __device__ __forceinline__ TreeHot load_hot(const TreeRec* G) {
     const uint4 b = reinterpret_cast<const uint4*>(G)[1];
     TreeHot T;
     T.n_nodes = (int)a.x; T.root_N = (int)a.y; T.root_W = __uint_as_float(a.z); T.sims_left = (int)a.w;
-    T.n_pending = (int)b.x; T.flags = b.z;
+    T.n_pending = (int)b.x; T.row = (int)b.y; T.flags = b.z;
     return T;
 }
 __device__ __forceinline__ void store_hot(TreeRec* G, const TreeHot& T) {
     reinterpret_cast<uint4*>(G)[0] = make_uint4((uint32_t)T.n_nodes, (uint32_t)T.root_N, __float_as_uint(T.root_W), (uint32_t)T.sims_left);
-    reinterpret_cast<uint2*>(G)[2] = make_uint2((uint32_t)T.n_pending, 0u);
+    reinterpret_cast<uint2*>(G)[2] = make_uint2((uint32_t)T.n_pending, (uint32_t)T.row);
     G->flags = T.flags;
 }
 
@@ -90,6 +92,16 @@ struct TreeArgs {
     int max_nodes;
     int stride;           // node stride in bytes
     double cpuct, cpuct_base;
+    // evaluation cache (utils/proxies.py:23-26,35-43): direct-mapped table of cache_mask + 1 entries of A 16-byte cells
+    // {p_a, key[3]}; the value rides in the cell of padding action `cache_vcell`.  nullptr = disabled.
+    uint4* cache;
+    uint32_t cache_mask;
+    int cache_vcell;
+    // lock-step bookkeeping, self-resetting (the last CTA of a launch publishes and zeroes it):
+    // ctr[0] rows handed out, ctr[1] trees still busy, ctr[2] CTAs done | ctr[4] rows of the last launch, ctr[5] busy trees
+    int* ctr;
+    int compact;          // 1: a tree's pending leaf goes to row atomicAdd(ctr[0]) instead of row == tree (pending == 1 only)
+    int max_inline;       // > 0: at most this many simulations per tree and launch may finish without the net
 };
 
 __device__ __forceinline__ char* node_ptr(const TreeArgs& ta, int t, int i) {
@@ -304,10 +316,14 @@ struct StepInputs {
     float value;
 };
 
+// `nrow` = row of the evaluator's batch (priors / values); the engine-owned pending record and path are indexed by
+// slot and tree.  nrow < 0: k * n_trees + t (the non-compact layout).
 template <int APL>
-__device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta, int t, int k, const float* __restrict__ priors,
-                                             const float* __restrict__ values, StepInputs<APL>& in, int lane) {
+__device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta, int t, int k, int64_t nrow,
+                                             const float* __restrict__ priors, const float* __restrict__ values,
+                                             StepInputs<APL>& in, int lane) {
     const int64_t row = (int64_t)k * ta.n_trees + t;
+    if (nrow < 0) nrow = row;
     const uint4* pr = ta.pend + row * 3;
     in.lh0 = pr[0]; in.lh1 = pr[1];
     const uint4 m = pr[2];
@@ -315,22 +331,86 @@ __device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta,
 #pragma unroll
     for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? ta.path[row * PATH_CAP + lane + 32 * i] : 0u;
 #pragma unroll
-    for (int q = 0; q < APL; ++q) { int a = lane + 32 * q; in.p[q] = a < b.A ? priors[row * b.A + a] : 0.0f; }
-    in.value = values[row];
+    for (int q = 0; q < APL; ++q) { int a = lane + 32 * q; in.p[q] = a < b.A ? priors[nrow * b.A + a] : 0.0f; }
+    in.value = values[nrow];
+}
+
+// ---- evaluation cache (the engine's form of AsyncBatchedProxy's LRU, utils/proxies.py:23-26,35-43).
+// Key = get_hash() = (edge set, boxes_to_close[to_play]) (dots_boxes_game.py:106-112): exactly what get_features()
+// shows the net, so a hit returns what the net would return.  The full 96-bit key sits in EVERY 16-byte cell next to
+// its 4 payload bytes and a lookup only hits when all A cells carry the probe's key; cells are written with single
+// 16-byte stores, so whatever races between trees of one launch (same key: same payload; different keys on one slot:
+// mixed cells) can only turn a hit into a miss, never into a wrong evaluation.
+struct CacheKey { uint32_t k0, k1, k2; uint32_t slot; };
+__device__ __forceinline__ CacheKey cache_key(const TreeArgs& ta, const Hdr& h) {
+    const int btc = h.to_play ? h.btc1 : h.btc0;
+    CacheKey k;
+    k.k0 = (uint32_t)h.e0; k.k1 = (uint32_t)(h.e0 >> 32);
+    k.k2 = ((uint32_t)h.e1 & 0xffffffu) | (((uint32_t)btc & 0xffu) << 24);  // A <= 88: e1 has at most 24 bits
+    uint64_t x = h.e0 * 0x9E3779B97F4A7C15ull ^ ((uint64_t)k.k2 + 0x632BE59BD9B4E019ull) * 0xC2B2AE3D27D4EB4Full;
+    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+    k.slot = (uint32_t)x & ta.cache_mask;
+    return k;
+}
+
+// probe for the leaf in in.lh0/lh1; on a hit in.p / in.value hold the cached net outputs
+template <int APL>
+__device__ __forceinline__ bool cache_lookup(const Board& b, const TreeArgs& ta, StepInputs<APL>& in, int lane) {
+    const Hdr h = unpack_hdr(in.lh0, in.lh1);
+    const CacheKey key = cache_key(ta, h);
+    const uint4* cells = ta.cache + (size_t)key.slot * (size_t)b.A;
+    uint4 c[APL];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+        const int a = lane + 32 * k;
+        if (a < b.A) {
+            c[k] = cells[a];
+            ok = ok && c[k].y == key.k0 && c[k].z == key.k1 && c[k].w == key.k2;
+        } else c[k] = make_uint4(0, 0, 0, 0);
+    }
+    if (!__all_sync(0xffffffffu, ok)) return false;
+    const int vl = ta.cache_vcell & 31, vk = ta.cache_vcell >> 5;
+    uint32_t vbits = 0;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+        in.p[k] = __uint_as_float(c[k].x);
+        if (k == vk) { vbits = c[k].x; if (lane == vl) in.p[k] = 0.0f; }  // a padding action: its prior is masked anyway
+    }
+    in.value = __uint_as_float(__shfl_sync(0xffffffffu, vbits, vl));
+    return true;
+}
+
+template <int APL>
+__device__ __forceinline__ void cache_insert(const Board& b, const TreeArgs& ta, const Hdr& lh, const StepInputs<APL>& in, int lane) {
+    const CacheKey key = cache_key(ta, lh);
+    uint4* cells = ta.cache + (size_t)key.slot * (size_t)b.A;
+#pragma unroll
+    for (int k = 0; k < APL; ++k) {
+        const int a = lane + 32 * k;
+        if (a < b.A) {
+            const float payload = (a == ta.cache_vcell) ? in.value : in.p[k];
+            cells[a] = make_uint4(__float_as_uint(payload), key.k0, key.k1, key.k2);
+        }
+    }
 }
 
 // expand + backup of one pending leaf (mcts.py:116-132 and the prior masking of 188-196).  The virtual loss was
 // subtracted by the selection that produced the path (mcts.py:109), so every path node just gets
 // W = fl32(W + fl32(v*s + 1)) and N += 1.
+// `src`: where in.p / in.value come from -- EV_NET (the evaluator: remembered in the eval cache if there is one),
+// EV_CACHE (a cache hit), EV_NONE (terminal leaf, no evaluation).
+enum { EV_NET = 0, EV_CACHE = 1, EV_NONE = 2 };
 template <int APL, int NW>
 __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArgs& ta, int t, TreeHot& T,
-                                                   const StepInputs<APL>& in, double* sh, int lane) {
+                                                   const StepInputs<APL>& in, double* sh, int lane, int src) {
     const int A = b.A;
     char* lp = node_ptr(ta, t, in.leaf);
     Hdr lh = unpack_hdr(in.lh0, in.lh1);
     const bool terminal = lh.flags & NF_TERMINAL;
     float value;
     if (!terminal) {
+        if (src == EV_NET && ta.cache) cache_insert<APL>(b, ta, lh, in, lane);
         // child_priors * valid (float32), NumPy-order sum, renormalise unless s == 1 or s <= 0
         float* shf = reinterpret_cast<float*>(sh);
         float p[APL];
@@ -401,6 +481,7 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
         if (terminal) { G->terminal_count += 1; G->total_term += 1; }
         if (lh.depth > G->max_deepness) G->max_deepness = lh.depth;
         G->total_sims += 1;
+        if (src == EV_CACHE) G->cache_hits += 1;
         G->total_path += plen;
     }
 }
@@ -565,33 +646,108 @@ k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, cons
     if (lane == 0) store_hot(ta.trees + t, T);
 }
 
+// Hand a selected leaf to the evaluator: planes / packed state into batch row `row`, the engine-side pending record
+// (header copy, node index, path length) into slot `prow`.
 template <int APL, int NW>
-__global__ void __launch_bounds__(TREE_WARPS * 32, APL == 1 ? 7 : (APL == 2 ? 5 : 3))
-k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this search, <= ta.max_pending */,
-              const float* __restrict__ priors, const float* __restrict__ values,
-              const double* __restrict__ noise, double coeff, void* __restrict__ planes, int dtype, int layout,
-              dbaz_state* __restrict__ leaf_states, int8_t* __restrict__ leaf_kind) {
-    __shared__ double sh_all[TREE_WARPS][DBAZ_MAX_ACTIONS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * TREE_WARPS + warp;
-    if (t >= ta.n_trees) return;
+__device__ __forceinline__ void emit_leaf(const Board& b, const TreeArgs& ta, const StepInputs<APL>& in, int64_t prow, int64_t row,
+                                          void* __restrict__ planes, int dtype, int layout, dbaz_state* __restrict__ leaf_states,
+                                          int lane) {
+    const Hdr lh = unpack_hdr(in.lh0, in.lh1);
+    write_planes_warp<NW>(b, hdr_edges<NW>(lh), (int)(int8_t)(lh.to_play ? lh.btc1 : lh.btc0), planes, row, dtype, layout, lane);
+    if (lane == 0) {
+        uint4* pr = ta.pend + prow * 3;
+        pr[0] = in.lh0; pr[1] = in.lh1; pr[2] = make_uint4((uint32_t)in.leaf, (uint32_t)in.plen, 0u, 0u);
+        if (leaf_states) {
+            Hdr pub = lh;
+            pub.flags = 0; pub.depth = 0; pub.parent = -1; pub.parent_action = -1;
+            store_hdr_regs(reinterpret_cast<char*>(&leaf_states[row]), pub);
+        }
+    }
+}
+
+// One tree's share of a lock-step wave.  Returns true while the tree still has work (a pending leaf or simulations left).
+template <int APL, int NW>
+__device__ __forceinline__ bool search_step_tree(const Board& b, const TreeArgs& ta, int t, int pending,
+                                                 const float* __restrict__ priors, const float* __restrict__ values,
+                                                 const double* __restrict__ noise, double coeff, void* __restrict__ planes,
+                                                 int dtype, int layout, dbaz_state* __restrict__ leaf_states,
+                                                 int8_t* __restrict__ leaf_kind, double* sh, int lane) {
     // ---- one round trip: everything whose address depends only on t
     TreeHot T = load_hot(ta.trees + t);
-    StepInputs<APL> in;
-    load_pending<APL>(b, ta, t, 0, priors, values, in, lane);
+    const bool compact = ta.compact && pending == 1;
     LaneActions<APL, NW> la;
     la.load(b, ta.act_tab, lane);
+    StepInputs<APL> in;
+    if (!compact) load_pending<APL>(b, ta, t, 0, -1, priors, values, in, lane);
 
     if (T.n_pending <= 0 && T.sims_left <= 0) {  // idle tree
-        if (leaf_kind) for (int r = lane; r < pending; r += 32) leaf_kind[(int64_t)r * ta.n_trees + t] = 0;
-        return;
+        if (leaf_kind && !compact) for (int r = lane; r < pending; r += 32) leaf_kind[(int64_t)r * ta.n_trees + t] = 0;
+        return false;
     }
-    double* sh = sh_all[warp];
-    // ---- the evaluations of the previous wave come back: expand + backup, in selection order
+    if (compact) load_pending<APL>(b, ta, t, 0, T.n_pending > 0 ? T.row : 0, priors, values, in, lane);
+
+    if (pending == 1) {
+        // ---- strictly sequential simulations (max_pending_evals = 1).  The evaluation of the previous wave comes
+        // back, then the tree runs on for as long as its simulations need no evaluator: terminal leaves
+        // (mcts.py:194-196) and leaves found in the eval cache (the proxy returns those without suspending,
+        // utils/proxies.py:35-38) complete on the spot; the first leaf that needs the net ends the wave.
+        if (T.n_pending > 0) {
+            tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane, EV_NET);
+            T.n_pending = 0;
+            T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);  // lane 0 owns the authoritative TreeRec
+            __syncwarp();
+            if (T.flags & TF_PREP_PENDING) {
+                dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
+                root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
+            }
+        }
+        T.flags &= ~TF_FIRST_WAVE;
+        uint32_t* path = ta.path + (int64_t)t * PATH_CAP;
+        int inline_done = 0;
+        while (T.sims_left > 0) {
+            __syncwarp();  // stores of the previous backup must be visible to this selection's loads
+            const int kind = tree_select<APL, NW>(b, ta, t, T, la, in, path, lane);
+            if (!kind) break;  // node pool exhausted
+            T.sims_left -= 1;
+            int src = EV_NONE;
+            if (kind == 1) {
+                if (ta.cache && cache_lookup<APL>(b, ta, in, lane)) src = EV_CACHE;
+                else {
+                    int64_t row = t;
+                    if (compact) {
+                        int r = 0;
+                        if (lane == 0) r = atomicAdd(&ta.ctr[0], 1);
+                        T.row = __shfl_sync(0xffffffffu, r, 0);
+                        row = T.row;
+                    }
+                    emit_leaf<APL, NW>(b, ta, in, t, row, planes, dtype, layout, leaf_states, lane);
+                    T.n_pending = 1;
+                    break;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? path[lane + 32 * i] : 0u;
+            tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane, src);
+            T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
+            if (src == EV_CACHE && (T.flags & TF_PREP_PENDING)) {
+                __syncwarp();
+                dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
+                root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
+            }
+            if (ta.max_inline > 0 && ++inline_done >= ta.max_inline) break;
+        }
+        if (leaf_kind && !compact && lane == 0) leaf_kind[t] = (int8_t)T.n_pending;
+        if (lane == 0) store_hot(ta.trees + t, T);
+        return T.n_pending > 0 || T.sims_left > 0;
+    }
+
+    // ---- max_pending_evals = K > 1: the reference's waves.  The evaluations of the previous wave come back:
+    // expand + backup, in selection order
     const int n_back = T.n_pending;
     for (int k = 0; k < n_back; ++k) {
-        if (k > 0) { __syncwarp(); load_pending<APL>(b, ta, t, k, priors, values, in, lane); }
-        tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane);
+        if (k > 0) { __syncwarp(); load_pending<APL>(b, ta, t, k, -1, priors, values, in, lane); }
+        tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane, EV_NONE);
     }
     T.n_pending = 0;
     if (n_back > 0) {
@@ -623,27 +779,50 @@ k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this sea
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? path[lane + 32 * i] : 0u;
-            tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane);
+            tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane, EV_NONE);
             T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
             continue;
         }
-        const Hdr lh = unpack_hdr(in.lh0, in.lh1);
-        write_planes_warp<NW>(b, hdr_edges<NW>(lh), (int)(int8_t)(lh.to_play ? lh.btc1 : lh.btc0), planes, row, dtype, layout, lane);
-        if (lane == 0) {
-            uint4* pr = ta.pend + row * 3;
-            pr[0] = in.lh0; pr[1] = in.lh1; pr[2] = make_uint4((uint32_t)in.leaf, (uint32_t)in.plen, 0u, 0u);
-            if (leaf_states) {
-                Hdr pub = lh;
-                pub.flags = 0; pub.depth = 0; pub.parent = -1; pub.parent_action = -1;
-                store_hdr_regs(reinterpret_cast<char*>(&leaf_states[row]), pub);
-            }
-            if (leaf_kind) leaf_kind[row] = 1;
-        }
+        emit_leaf<APL, NW>(b, ta, in, row, row, planes, dtype, layout, leaf_states, lane);
+        if (leaf_kind && lane == 0) leaf_kind[row] = 1;
         ++n_out;
     }
     T.n_pending = n_out;
     if (leaf_kind) for (int r = lane; r < pending; r += 32) if (r >= n_out) leaf_kind[(int64_t)r * ta.n_trees + t] = 0;
     if (lane == 0) store_hot(ta.trees + t, T);
+    return T.n_pending > 0 || T.sims_left > 0;
+}
+
+template <int APL, int NW>
+__global__ void __launch_bounds__(TREE_WARPS * 32, APL == 1 ? 7 : (APL == 2 ? 5 : 3))
+k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this search, <= ta.max_pending */,
+              const float* __restrict__ priors, const float* __restrict__ values,
+              const double* __restrict__ noise, double coeff, void* __restrict__ planes, int dtype, int layout,
+              dbaz_state* __restrict__ leaf_states, int8_t* __restrict__ leaf_kind) {
+    __shared__ double sh_all[TREE_WARPS][DBAZ_MAX_ACTIONS];
+    __shared__ int s_busy[TREE_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * TREE_WARPS + warp;
+    bool busy = false;
+    if (t < ta.n_trees)
+        busy = search_step_tree<APL, NW>(b, ta, t, pending, priors, values, noise, coeff, planes, dtype, layout, leaf_states,
+                                         leaf_kind, sh_all[warp], lane);
+    // ---- wave bookkeeping: the last CTA to finish publishes {rows handed out, busy trees} and re-arms the counters
+    if (lane == 0) s_busy[warp] = busy ? 1 : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nb = 0;
+#pragma unroll
+        for (int w = 0; w < TREE_WARPS; ++w) nb += s_busy[w];
+        if (nb) atomicAdd(&ta.ctr[1], nb);
+        __threadfence();
+        if (atomicAdd(&ta.ctr[2], 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            ta.ctr[4] = atomicExch(&ta.ctr[0], 0);
+            ta.ctr[5] = atomicExch(&ta.ctr[1], 0);
+            ta.ctr[2] = 0;
+        }
+    }
 }
 
 // UCT_search's time limit (mcts.py:232-233): launch no further simulations; pending leaves still back up
@@ -667,9 +846,9 @@ __global__ void k_reset_roots(Board b, TreeArgs ta, const dbaz_state* __restrict
     s.parent = -1; s.parent_action = -1; s.result = (int16_t)r;
     store_hdr(node_ptr(ta, t, 0), s);
     TreeRec T;
-    T.n_nodes = 1; T.root_N = 0; T.root_W = 0.0f; T.sims_left = 0; T.n_pending = 0; T.reserved_ = 0; T.flags = 0;
+    T.n_nodes = 1; T.root_N = 0; T.root_W = 0.0f; T.sims_left = 0; T.n_pending = 0; T.row = 0; T.flags = 0;
     T.max_deepness = 0; T.deepness_correction = 0; T.terminal_count = 0; T.tree_size = 0; T.total_term = 0;
-    T.total_sims = 0; T.total_path = 0;
+    T.total_sims = 0; T.cache_hits = 0; T.total_path = 0;
     ta.trees[t] = T;
 }
 
@@ -882,7 +1061,8 @@ __global__ void k_status(TreeArgs ta, unsigned long long* __restrict__ out4) {
     if (t >= ta.n_trees) return;
     TreeRec T = ta.trees[t];
     if (T.flags & (TF_ERR_POOL | TF_ERR_MOVE)) atomicAdd(&out4[0], 1ull);
-    atomicAdd(&out4[1], T.total_sims);
+    atomicAdd(&out4[1], (unsigned long long)T.total_sims);
+    atomicAdd(&out4[5], (unsigned long long)T.cache_hits);
     atomicAdd(&out4[2], T.total_path);
     atomicMax(&out4[3], (unsigned long long)T.n_nodes);
     atomicAdd(&out4[4], (unsigned long long)T.total_term);

@@ -29,7 +29,8 @@ class Engine:
     States are device tensors of shape [n, 4] int64 (32 packed bytes each, see STATE_DTYPE).
     """
 
-    def __init__(self, board=(3, 3), n_games=1, max_nodes=8192, cpuct=(1.25, 19652), device=None, lut_size=0, max_pending=1):
+    def __init__(self, board=(3, 3), n_games=1, max_nodes=8192, cpuct=(1.25, 19652), device=None, lut_size=0, max_pending=1,
+                 eval_cache=0):
         if not torch.cuda.is_available():
             raise RuntimeError("dotsboxesaz_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _capi.load()
@@ -59,6 +60,7 @@ class Engine:
         self._leaf_states = torch.zeros((cap, 4), dtype=torch.int64, device=self.device)
         self._leaf_kind = torch.zeros((cap,), dtype=torch.int8, device=self.device)
         self.pending = 1
+        self._batch_rows = None      # evaluator batch of the adaptive wave loop (None: pending * n_games)
         self._planes = None
         self._plane_cfg = None
         self._noise = None  # keeps the caller's noise buffer alive while the engine may read it
@@ -69,6 +71,16 @@ class Engine:
         self.n_launches = 0  # engine kernels enqueued (graph replays count the kernels they contain)
         self.set_planes(torch.float32, channels_last=False)
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        # lock-step scheduling state (see set_mode / run_search(adaptive=True))
+        self.compact = False
+        self.max_inline = 0
+        self.set_mode(False, 4)
+        self.eval_cache_log2 = 0
+        self._counts_host = torch.zeros((64, 2), dtype=torch.int32).pin_memory()
+        self._graph_pool = None
+        self.n_waves = 0             # dbaz_search_step launches (graph replays count the waves they contain)
+        if eval_cache:
+            self.set_eval_cache(eval_cache)
 
     # ------------------------------------------------------------ plumbing
     def close(self):
@@ -105,8 +117,36 @@ class Engine:
 
     @property
     def n_rows(self):
-        """Leaf rows of the current search: max_pending_evals * n_games."""
-        return self.pending * self.n_games
+        """Leaf rows the evaluator works on: max_pending_evals * n_games, or the (smaller) batch the adaptive wave
+        loop of run_search() currently runs at."""
+        return self.pending * self.n_games if self._batch_rows is None else self._batch_rows
+
+    # ------------------------------------------- eval cache / scheduling mode
+    def set_eval_cache(self, log2_entries):
+        """Device table of 2**log2_entries cached evaluations keyed by get_hash() -- the engine's form of
+        AsyncBatchedProxy's LRU (utils/proxies.py:23-26,35-43); 0 frees it.  Synchronises."""
+        self._ck(self.lib.dbaz_cache_configure(self._h, int(log2_entries)), launches=0)
+        self.eval_cache_log2 = int(log2_entries)
+        self._graphs = {}  # captured step kernels carry the table pointer
+        self._graph_pool = None  # the pool dies with its last graph
+
+    def clear_eval_cache(self):
+        """Forget all cached evaluations (after a weight update)."""
+        self._ck(self.lib.dbaz_cache_clear(self._h, self._stream()), launches=0)
+
+    def set_mode(self, compact=False, max_inline=0):
+        """compact: leaves go to consecutive batch rows (see include/dbaz_b200.h); max_inline: bound on the
+        simulations per tree and wave that finish without the evaluator (0 = unbounded)."""
+        if (bool(compact), int(max_inline)) != (self.compact, self.max_inline):
+            self._ck(self.lib.dbaz_search_set_mode(self._h, 1 if compact else 0, int(max_inline)), launches=0)
+            self.compact, self.max_inline = bool(compact), int(max_inline)
+
+    def wave_counts(self):
+        """(rows handed to the evaluator, busy trees) of the last step.  Synchronises the stream."""
+        buf = self._counts_host[0]
+        self._ck(self.lib.dbaz_search_wave_counts(self._h, C.c_void_p(buf.data_ptr()), self._stream()), launches=0)
+        torch.cuda.current_stream(self.device).synchronize()
+        return int(buf[0]), int(buf[1])
 
     @property
     def priors(self):
@@ -284,20 +324,28 @@ class Engine:
         self._ck(self.lib.dbaz_search_step(self._h, _ptr(self._priors), _ptr(self._values), _ptr(self._planes_base),
                                            _DTYPE_CODE[dtype], _capi.NHWC if cl else _capi.NCHW, _ptr(self._leaf_states),
                                            _ptr(self._leaf_kind), self._stream()))
+        self.n_waves += 1
 
     def step_flush(self):
         """Stop launching simulations (UCT_search's time limit) and back up the pending leaves."""
         self._ck(self.lib.dbaz_search_stop(self._h, self._stream()))
         self.step()
 
-    def run_search(self, num_reads, evaluator, noise=None, coeff=0.0, max_reads=None, graph_waves=0, pending=1):
+    def run_search(self, num_reads, evaluator, noise=None, coeff=0.0, max_reads=None, graph_waves=0, pending=1, adaptive=False):
         """UCT_search for all trees.  `evaluator(engine)` must fill engine.priors / engine.values for the
         leaves in engine.planes / engine.leaf_states, on the current stream, without host sync.
 
         pending: max_pending_evals (simulations in flight per tree, see begin()).
         graph_waves > 0: `graph_waves` consecutive [step kernel -> evaluator] waves are captured once in a
         CUDA graph and replayed, so the 800-wave inner loop costs one launch per `graph_waves` waves.
-        Surplus waves at the end of the last replay are no-ops for trees that have finished."""
+        Surplus waves at the end of the last replay are no-ops for trees that have finished.
+
+        adaptive (pending == 1, graph_waves > 0): instead of a fixed number of full-width waves, the loop runs until
+        no tree has work left and shrinks the evaluator's batch as trees finish -- see _run_adaptive()."""
+        if adaptive and int(pending) == 1 and graph_waves > 0:
+            return self._run_adaptive(num_reads, evaluator, noise, coeff, graph_waves)
+        if self.compact:
+            self.set_mode(False, self.max_inline)
         if max_reads is None:
             max_reads = int(num_reads) if isinstance(num_reads, int) else int(torch.as_tensor(num_reads).max())
         pending = int(pending)
@@ -312,7 +360,7 @@ class Engine:
                     self._noise_buf = torch.zeros((self.n_games, self.A), dtype=torch.float64, device=self.device)
                 self._noise_buf.copy_(torch.as_tensor(noise, dtype=torch.float64).reshape(self.n_games, self.A))
                 noise = self._noise_buf
-            key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, pending)
+            key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, pending, self._mode_key())
             if key not in self._graphs:
                 # the evaluator is stored next to its graph: a live reference keeps id() from being recycled
                 self._graphs[key] = (self._capture(evaluator, graph_waves, noise, coeff, pending), evaluator)
@@ -322,12 +370,72 @@ class Engine:
             for _ in range((waves + graph_waves - 1) // graph_waves):
                 g.replay()
                 self.n_launches += graph_waves * per_wave
+                self.n_waves += graph_waves
         else:
             self.begin(num_reads, noise, coeff, pending)
             for _ in range(waves):
                 self.step()
                 evaluator(self)
         self.step()  # flush the last backup
+
+    # batch sizes of the adaptive loop, as fractions of n_games (each one is a captured graph)
+    LADDER = (1.0, 0.75, 0.5, 0.375, 0.25, 0.125, 0.0625, 0.03125)
+
+    def _ladder(self):
+        rows = sorted({max(min(self.n_games, 64), -(-int(self.n_games * f) // 8) * 8) for f in self.LADDER}, reverse=True)
+        return [min(r, self.n_games) for r in rows]
+
+    def _run_adaptive(self, num_reads, evaluator, noise, coeff, graph_waves):
+        """The wave loop with a shrinking evaluator batch.  Leaves are handed over in compact rows (set_mode), the step
+        kernel publishes how many trees still have work, and the host -- one graph replay behind the device -- picks
+        the smallest captured batch that holds them (the count never grows during a search, so a stale value is
+        safe) and stops when it reads zero.  The decision for replay i+2 is taken from the count at the end of
+        replay i, which the host waits for: the schedule, and with it every evaluator batch, is reproducible."""
+        self.pending = 1
+        self.set_mode(True, self.max_inline)
+        if noise is not None:
+            if self._noise_buf is None:
+                self._noise_buf = torch.zeros((self.n_games, self.A), dtype=torch.float64, device=self.device)
+            self._noise_buf.copy_(torch.as_tensor(noise, dtype=torch.float64).reshape(self.n_games, self.A))
+            noise = self._noise_buf
+        ladder = self._ladder()
+        per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
+        key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, 1, self._mode_key(), "ladder")
+        if key not in self._graphs:
+            # every batch size is captured up front: capturing re-binds the search head and idles all trees
+            graphs = {}
+            for rows in ladder:
+                self._batch_rows = rows
+                try:
+                    graphs[rows] = self._capture(evaluator, graph_waves, noise, coeff, 1)
+                finally:
+                    self._batch_rows = None
+            self._graphs[key] = (graphs, evaluator)
+        graphs = self._graphs[key][0]
+        self.begin(num_reads, noise, coeff, 1)
+        stream = torch.cuda.current_stream(self.device)
+        events = []
+        rows, i = ladder[0], 0
+        while True:
+            graphs[rows].replay()
+            self.n_launches += graph_waves * per_wave
+            self.n_waves += graph_waves
+            slot = self._counts_host[i % self._counts_host.shape[0]]
+            self.lib.dbaz_search_wave_counts(self._h, C.c_void_p(slot.data_ptr()), self._stream())
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            events.append((ev, slot))
+            i += 1
+            if len(events) >= 2:
+                ev0, slot0 = events.pop(0)
+                ev0.synchronize()
+                busy = int(slot0[1])
+                if busy == 0:
+                    break
+                rows = min(r for r in ladder if r >= busy)
+
+    def _mode_key(self):
+        return (self.compact, self.max_inline, self.eval_cache_log2)
 
     def _capture(self, evaluator, graph_waves, noise, coeff, pending=1):
         # warm up the evaluator alone (allocator, cuDNN heuristics); no leaf is pending between searches,
@@ -344,12 +452,14 @@ class Engine:
         self._noise = noise
         self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), int(pending), _ptr(noise), float(coeff), self._stream())
         g = torch.cuda.CUDAGraph()
-        n0 = self.n_launches
-        with torch.cuda.graph(g):
+        n0, w0 = self.n_launches, self.n_waves
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()  # graphs never run concurrently and keep nothing alive
+        with torch.cuda.graph(g, pool=self._graph_pool):
             for _ in range(graph_waves):
                 self.step()
                 evaluator(self)
-        self.n_launches = n0  # capture enqueues nothing
+        self.n_launches, self.n_waves = n0, w0  # capture enqueues nothing
         return g
 
     def root_visits(self):
@@ -394,7 +504,8 @@ class Engine:
         """Synchronises.  Returns dict(errors, sims, path_nodes, max_nodes_used); raises if a tree faulted."""
         out = (C.c_int64 * 8)()
         rc = self.lib.dbaz_search_status(self._h, out, self._stream())
-        d = {"errors": out[0], "sims": out[1], "path_nodes": out[2], "max_nodes_used": out[3], "terminal_leaves": out[4]}
+        d = {"errors": out[0], "sims": out[1], "path_nodes": out[2], "max_nodes_used": out[3], "terminal_leaves": out[4],
+             "cache_hits": out[5]}
         if rc != 0:
             raise EngineError(self.lib.dbaz_last_error(self._h).decode())
         return d

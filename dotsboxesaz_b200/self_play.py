@@ -136,11 +136,14 @@ class BatchedSelfPlay:
     Dirichlet draw (if alpha > 0) and then the uniform of np.random.choice, the reference's order.
     """
 
-    def __init__(self, engine, evaluator, params, graph_waves=16, pending=None):
+    def __init__(self, engine, evaluator, params, graph_waves=16, pending=None, adaptive=None):
         self.eng = engine
         self.ev = evaluator
         self.params = params
         self.graph_waves = graph_waves
+        # adaptive wave loop (Engine.run_search): on by default when the engine has an eval cache, where the number of
+        # waves a search needs is not known in advance
+        self.adaptive = bool(engine.eval_cache_log2) if adaptive is None else bool(adaptive)
         # simulations in flight per tree: the reference's max_async_searches, capped by what the engine was built for
         want = params.self_play.mcts.max_async_searches if pending is None else pending
         self.pending = max(1, min(int(want or 1), engine.max_pending))
@@ -186,7 +189,8 @@ class BatchedSelfPlay:
                 if alpha > 0:
                     noise[g] = rngs[g].dirichlet(np.ones(A) * alpha, 1).ravel() * valid[g]
             eng.run_search(torch.from_numpy(reads), self.ev, noise=None if noise is None else torch.from_numpy(noise),
-                           coeff=coeff, max_reads=int(reads.max()), graph_waves=self.graph_waves, pending=self.pending)
+                           coeff=coeff, max_reads=int(reads.max()), graph_waves=self.graph_waves, pending=self.pending,
+                           adaptive=self.adaptive)
             vis = eng.root_visits().cpu().numpy()
             stats, _rW, q = (x.cpu().numpy() for x in eng.tree_stats())
             moves = np.full(n, -1, dtype=np.int32)
@@ -255,7 +259,7 @@ class BatchedSelfPlay:
                                 torch.full((n,), -1, dtype=torch.int32, device=dev))
             noise = noise_all[move_i] * valid if noise_all is not None else None
             eng.run_search(reads, self.ev, noise=noise, coeff=coeff, max_reads=_n_searches(k, num_read), graph_waves=self.graph_waves,
-                           pending=self.pending)
+                           pending=self.pending, adaptive=self.adaptive)
             vis = eng.root_visits()
             stats, _rw, q = eng.tree_stats()
             v = vis.double()

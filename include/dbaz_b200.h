@@ -144,9 +144,33 @@ int dbaz_search_root_states(dbaz_engine *e, dbaz_state *out, uint64_t stream);
  * reuse != 0 the chosen child's subtree is kept (compacted in place), else a fresh root. */
 int dbaz_search_advance_roots(dbaz_engine *e, const int32_t *moves, int32_t reuse, uint64_t stream);
 /* Synchronises `stream`.  out int64[8] = {trees with an error flag, total sims, total path nodes,
- * max n_nodes, terminal leaves, 0, 0, 0} (totals since reset_roots).  Returns non-zero (and sets
+ * max n_nodes, terminal leaves, eval-cache hits, 0, 0} (totals since reset_roots).  Returns non-zero (and sets
  * last_error) if any tree faulted. */
 int dbaz_search_status(dbaz_engine *e, int64_t *out8, uint64_t stream);
+
+/* ---- lock-step scheduling extras (max_pending_evals == 1 searches) ----
+ * compact != 0: the leaf a tree hands to the evaluator goes to the next free row of the batch (rows 0..n-1 are the
+ * n leaves of the wave, in no particular order) instead of row == tree, so the evaluator only has to run as many rows
+ * as there are busy trees; leaf_kind is not written in this mode.  max_inline > 0 bounds how many simulations of one
+ * tree may complete inside one dbaz_search_step() without the evaluator (terminal leaves, eval-cache hits); 0 = no
+ * bound: a tree runs on until a leaf needs the net (the order of a tree's simulations, hence every result, is the
+ * same for any setting). */
+int dbaz_search_set_mode(dbaz_engine *e, int32_t compact, int32_t max_inline);
+/* Enqueues a copy of {rows handed to the evaluator, trees that still have work} of the most recent
+ * dbaz_search_step() on `stream` into out2 (int32[2], device or pinned host memory).  The busy-tree count never
+ * grows during a search, so a stale value is a safe upper bound of the next wave's rows. */
+int dbaz_search_wave_counts(dbaz_engine *e, int32_t *out2, uint64_t stream);
+
+/* ---- evaluation cache: the engine's form of AsyncBatchedProxy's LRU (utils/proxies.py:23-26,35-43) ----
+ * A direct-mapped device table of 2^log2_entries entries (16*A bytes each) keyed by get_hash() = (edge set,
+ * boxes_to_close[to_play]) (dots_boxes_game.py:106-112), shared by all trees of the engine.  The step kernel
+ * stores every (priors, value) the evaluator returns and, for max_pending_evals == 1 searches, completes a
+ * simulation whose leaf is found in the table on the spot -- as the reference's proxy returns a cached result
+ * without suspending.  Keys are compared exactly (96 bits), so a hit always returns an evaluation of the same
+ * features.  log2_entries == 0 frees the table.  Synchronises the device.  Boards with A <= 88 only. */
+int dbaz_cache_configure(dbaz_engine *e, int32_t log2_entries);
+/* Forget every entry (call after the net's weights change). */
+int dbaz_cache_clear(dbaz_engine *e, uint64_t stream);
 
 /* ---- leaf-evaluation pipeline: fused elementwise stages between the library GEMMs/convs ----
  * (replaces the separate bias / ReLU / eval-BatchNorm / softmax passes of NeuralNetWrapper.predict_sync,

@@ -23,6 +23,10 @@ def main():
     ap.add_argument("--repeats", type=int, default=1)
     ap.add_argument("--pending", type=int, default=1, help="max_async_searches (simulations in flight per tree)")
     ap.add_argument("--no-warmup", action="store_true")
+    ap.add_argument("--eval-cache", type=int, default=0, help="log2(entries) of the device eval cache; 0 = off")
+    ap.add_argument("--max-inline", type=int, default=4)
+    ap.add_argument("--adaptive", type=int, default=-1, help="1/0 adaptive wave loop; -1 = on iff the cache is on")
+    ap.add_argument("--keep-cache", action="store_true", help="do not empty the cache between repeats (weights are fixed)")
     args = ap.parse_args()
     import torch
     from dotsboxesaz_b200 import engine, self_play
@@ -30,7 +34,9 @@ def main():
     from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
     from dotsboxesaz_b200.utils.utils import DotDict
     L, C = (int(x) for x in args.board.split("x"))
-    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.max_nodes, max_pending=args.pending)
+    eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.max_nodes, max_pending=args.pending,
+                        eval_cache=args.eval_cache if args.pending == 1 else 0)
+    eng.set_mode(False, args.max_inline)
     torch.manual_seed(0)
     if args.net == "fake":
         ev = engine.FakeNetEvaluator(0)
@@ -42,7 +48,10 @@ def main():
                                     "mcts": {"mcts_num_read": args.sims, "mcts_cpuct": (1.25, 19652),
                                              "temperature": {0: 1.0, 12: 0.02}, "max_async_searches": args.pending}}})
     for rep in range(args.repeats + 1):  # first pass warms up (graphs, cuDNN)
-        sp = self_play.BatchedSelfPlay(eng, ev, params, graph_waves=16)
+        sp = self_play.BatchedSelfPlay(eng, ev, params, graph_waves=16, adaptive=None if args.adaptive < 0 else bool(args.adaptive))
+        if not args.keep_cache:
+            eng.clear_eval_cache()
+        w0 = eng.n_waves
         torch.cuda.synchronize()
         t0 = time.time()
         if args.mode == "device":
@@ -57,6 +66,8 @@ def main():
         if rep == 0 and not args.no_warmup:
             continue
         print(json.dumps({"board": args.board, "games": args.games, "sims_per_move": args.sims, "net": args.net, "mode": args.mode, "max_pending_evals": args.pending,
+                          "eval_cache_log2": args.eval_cache, "max_inline": args.max_inline, "adaptive": sp.adaptive, "waves": eng.n_waves - w0,
+                          "cache_hit_frac": info.get("cache_hits", 0) / max(1, info["sims"]),
                           "seconds": dt, "games_per_hour": args.games / dt * 3600, "sims_per_sec": info["sims"] / dt,
                           "total_sims": info["sims"], "sample_rows": rows, "max_nodes_used": info["max_nodes_used"],
                           "mean_path_nodes": info["path_nodes"] / max(1, info["sims"]),
