@@ -42,15 +42,16 @@ def parse_args():
     ap.add_argument("--net-dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--net-plan", default="fused", choices=["fused", "module"],
                     help="fused: library convs/GEMMs + the engine's fused epilogue kernels; module: the plain nn.Module")
-    ap.add_argument("--graph-waves", type=int, default=16)
+    ap.add_argument("--graph-waves", type=int, default=8)
     ap.add_argument("--pending", type=int, default=1,
                     help="max_pending_evals: simulations in flight per tree (1 = strictly sequential, BASELINE configs[1]; "
                          "the reference ships 64, configuration.py:35)")
-    ap.add_argument("--eval-cache", type=int, default=22,
+    ap.add_argument("--eval-cache", type=int, default=24,
                     help="log2(entries) of the device eval cache (the reference's LRU of net outputs, utils/proxies.py:23-26); "
                          "emptied at the start of EVERY step, inside the timed region; 0 = off")
     ap.add_argument("--no-adaptive", action="store_true", help="fixed number of full-width waves instead of the adaptive loop")
     ap.add_argument("--max-inline", type=int, default=4, help="bound on simulations per tree and wave finished without the net")
+    ap.add_argument("--ladder-steps", type=int, default=16, help="evaluator batch sizes of the adaptive loop: games * k / steps")
     ap.add_argument("--no-ablation", action="store_true", help="skip the extra no-cache measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="processes for the CPU baseline (0 = min(cores-1, 64))")
@@ -234,6 +235,7 @@ def main():
     eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.sims + 8, device=dev, max_pending=args.pending,
                         eval_cache=use_cache)
     eng.set_mode(False, args.max_inline)
+    eng.LADDER_STEPS = args.ladder_steps
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.net_dtype]
     if args.net == "fake":
         ev = engine.FakeNetEvaluator(0)

@@ -390,6 +390,7 @@ int dbaz_search_begin(dbaz_engine* e, const int32_t* num_reads, int32_t pending,
     if (pending < 1 || pending > e->ta.max_pending) return fail(e, "pending must be in [1, max_pending of the engine]");
     DeviceGuard guard(e->cfg.device);
     e->noise = noise; e->coeff = coeff; e->pending = pending;
+    DBAZ_CK(e, cudaMemsetAsync(e->ta.ctr + 4, 0, 2 * sizeof(int), S(stream)));  // k_search_begin counts the busy trees into ctr[5]
     const int grid = blocks_for(e->ta.n_trees, TREE_WARPS);
     DBAZ_DISPATCH(e, (k_search_begin<APL, NW><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(e->board, e->ta, num_reads, noise, coeff)));
     return launch_ok(e, "k_search_begin");

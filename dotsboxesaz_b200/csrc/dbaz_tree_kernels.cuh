@@ -643,7 +643,10 @@ k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, cons
             T.sims_left = nr + 1;
         }
     }
-    if (lane == 0) store_hot(ta.trees + t, T);
+    if (lane == 0) {
+        store_hot(ta.trees + t, T);
+        if (T.sims_left > 0) atomicAdd(&ta.ctr[5], 1);  // busy trees at the start of the search (zeroed by the host)
+    }
 }
 
 // Hand a selected leaf to the evaluator: planes / packed state into batch row `row`, the engine-side pending record

@@ -378,12 +378,20 @@ class Engine:
                 evaluator(self)
         self.step()  # flush the last backup
 
-    # batch sizes of the adaptive loop, as fractions of n_games (each one is a captured graph)
-    LADDER = (1.0, 0.75, 0.5, 0.375, 0.25, 0.125, 0.0625, 0.03125)
+    # batch sizes of the adaptive loop (each one is a captured graph): n_games * k / LADDER_STEPS for k = LADDER_STEPS..1,
+    # then halvings down to 64 rows
+    LADDER_STEPS = 8
 
     def _ladder(self):
-        rows = sorted({max(min(self.n_games, 64), -(-int(self.n_games * f) // 8) * 8) for f in self.LADDER}, reverse=True)
-        return [min(r, self.n_games) for r in rows]
+        n, steps = self.n_games, max(1, int(self.LADDER_STEPS))
+        rows = {n}
+        for k in range(1, steps + 1):
+            rows.add(min(n, max(64, -(-(n * k // steps) // 8) * 8)))
+        r = n // steps
+        while r > 64:
+            r //= 2
+            rows.add(min(n, max(64, -(-r // 8) * 8)))
+        return sorted(rows, reverse=True)
 
     def _run_adaptive(self, num_reads, evaluator, noise, coeff, graph_waves):
         """The wave loop with a shrinking evaluator batch.  Leaves are handed over in compact rows (set_mode), the step
@@ -400,7 +408,7 @@ class Engine:
             noise = self._noise_buf
         ladder = self._ladder()
         per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
-        key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, 1, self._mode_key(), "ladder")
+        key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, 1, self._mode_key(), "ladder", self.LADDER_STEPS)
         if key not in self._graphs:
             # every batch size is captured up front: capturing re-binds the search head and idles all trees
             graphs = {}
@@ -415,7 +423,10 @@ class Engine:
         self.begin(num_reads, noise, coeff, 1)
         stream = torch.cuda.current_stream(self.device)
         events = []
-        rows, i = ladder[0], 0
+        busy = self.wave_counts()[1]  # trees that take part in this search (begin() counted them)
+        if busy == 0:
+            return
+        rows, i = min(r for r in ladder if r >= busy), 0
         while True:
             graphs[rows].replay()
             self.n_launches += graph_waves * per_wave

@@ -157,7 +157,7 @@ int dbaz_search_status(dbaz_engine *e, int64_t *out8, uint64_t stream);
  * same for any setting). */
 int dbaz_search_set_mode(dbaz_engine *e, int32_t compact, int32_t max_inline);
 /* Enqueues a copy of {rows handed to the evaluator, trees that still have work} of the most recent
- * dbaz_search_step() on `stream` into out2 (int32[2], device or pinned host memory).  The busy-tree count never
+ * dbaz_search_step() (after dbaz_search_begin(): {0, trees with simulations to run}) on `stream` into out2 (int32[2], device or pinned host memory).  The busy-tree count never
  * grows during a search, so a stale value is a safe upper bound of the next wave's rows. */
 int dbaz_search_wave_counts(dbaz_engine *e, int32_t *out2, uint64_t stream);
 

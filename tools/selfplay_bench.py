@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--eval-cache", type=int, default=0, help="log2(entries) of the device eval cache; 0 = off")
     ap.add_argument("--max-inline", type=int, default=4)
     ap.add_argument("--adaptive", type=int, default=-1, help="1/0 adaptive wave loop; -1 = on iff the cache is on")
+    ap.add_argument("--graph-waves", type=int, default=8)
+    ap.add_argument("--ladder-steps", type=int, default=16)
     ap.add_argument("--keep-cache", action="store_true", help="do not empty the cache between repeats (weights are fixed)")
     args = ap.parse_args()
     import torch
@@ -37,6 +39,7 @@ def main():
     eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.max_nodes, max_pending=args.pending,
                         eval_cache=args.eval_cache if args.pending == 1 else 0)
     eng.set_mode(False, args.max_inline)
+    eng.LADDER_STEPS = args.ladder_steps
     torch.manual_seed(0)
     if args.net == "fake":
         ev = engine.FakeNetEvaluator(0)
@@ -48,7 +51,7 @@ def main():
                                     "mcts": {"mcts_num_read": args.sims, "mcts_cpuct": (1.25, 19652),
                                              "temperature": {0: 1.0, 12: 0.02}, "max_async_searches": args.pending}}})
     for rep in range(args.repeats + 1):  # first pass warms up (graphs, cuDNN)
-        sp = self_play.BatchedSelfPlay(eng, ev, params, graph_waves=16, adaptive=None if args.adaptive < 0 else bool(args.adaptive))
+        sp = self_play.BatchedSelfPlay(eng, ev, params, graph_waves=args.graph_waves, adaptive=None if args.adaptive < 0 else bool(args.adaptive))
         if not args.keep_cache:
             eng.clear_eval_cache()
         w0 = eng.n_waves
