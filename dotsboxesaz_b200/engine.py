@@ -427,7 +427,9 @@ class Engine:
         if busy == 0:
             return
         rows, i = min(r for r in ladder if r >= busy), 0
+        self.last_schedule = []  # (evaluator batch, busy trees it was chosen for) per replay, for profiling
         while True:
+            self.last_schedule.append((rows, busy))
             graphs[rows].replay()
             self.n_launches += graph_waves * per_wave
             self.n_waves += graph_waves

@@ -336,58 +336,105 @@ def _stem_tables(conv, rows, cols, in_scale=None, in_shift=None):
     return w01, to_pos(b), to_pos(k2)
 
 
-class FusedSimpleNN:
-    """Inference plan for SimpleNN (dots_boxes_nn.py:61-98): cuDNN convs / cuBLAS GEMMs on NHWC tensors with
-    the engine's fused epilogue kernel (bias + ReLU + BN in one pass) between them, fc0's columns permuted to
-    the NHWC flatten order, policy and value heads as ONE GEMM whose softmax / tanh write the engine's
-    float32 buffers directly.  Same function as the module in eval mode up to rounding of the compute dtype."""
+_ONE = (1, 1)
 
-    engine_launches = 8  # stem + 6 epilogues + 1 heads kernel per wave
+
+def _conv_relu(x, w, b, pad):
+    """relu(conv(x, w) + b) as ONE library kernel (cuDNN's fused conv-bias-activation; same speed as the bare conv)."""
+    return torch.cudnn_convolution_relu(x, w, b, _ONE, pad, _ONE, 1)
+
+
+def _conv_add_relu(x, w, z, b, pad):
+    """relu(conv(x, w) + z + b) as ONE library kernel (z has the shape of the output)."""
+    return torch.cudnn_convolution_add_relu(x, w, z, 1.0, b, _ONE, pad, _ONE, 1)
+
+
+def _cl(w, dtype):
+    return w.to(dtype).contiguous(memory_format=torch.channels_last)
+
+
+class FusedSimpleNN:
+    """Inference plan for SimpleNN (dots_boxes_nn.py:61-98), 9 kernels per batch instead of the module's ~45.
+
+    Every layer is conv/linear -> ReLU -> eval-mode BatchNorm (y = s*r + t).  The affine is pushed into the NEXT
+    layer: its weights take the factor s per input channel and its bias takes the image of t -- a constant vector for
+    the unpadded conv4 and the linear layers, a per-position map for the zero-padded 3x3 convs (the border sees fewer
+    taps), which is added as the `z` operand of cuDNN's fused conv-add-bias-ReLU.  So each layer is ONE library
+    kernel on the tensor cores with its bias/ReLU in the epilogue: cuDNN conv-(add-)bias-ReLU for the trunk,
+    cuBLASLt GEMM-bias-ReLU for the FC layers; conv0 (leaf gather + conv + ReLU straight from the packed leaf states)
+    and the softmax/tanh heads are the engine's own kernels.  fc0's columns are permuted to the NHWC flatten order,
+    policy and value heads are one GEMM.  Same function as the module in eval mode up to rounding of the compute
+    dtype (tests/test_gpu_nn.py)."""
 
     def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True):
         self.engine, self.dtype = engine, dtype
         dev = engine.device
         model = model.to(dev).train(False)
-        self.convs = []
+        rows, cols = engine.rows, engine.cols
+        cap = engine.n_games * engine.max_pending
         self.stem = None
-        if use_stem and dtype in (torch.bfloat16, torch.float16) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5)):
-            s0, t0 = _bn_affine(model.bn0)
-            self.stem = _stem_tables(model.conv0, engine.rows, engine.cols) + (s0, t0)
-            self.stem_out = torch.empty((engine.n_games * engine.max_pending, engine.rows, engine.cols, model.conv0.out_channels), dtype=dtype, device=dev)
-        for i in range(1 if self.stem is not None else 0, 5):
-            conv, bn = getattr(model, f"conv{i}"), getattr(model, f"bn{i}")
-            w = conv.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last)
-            s, t = _bn_affine(bn)
-            self.convs.append((w, conv.bias.detach().float().contiguous(), s, t, conv.padding))
-        c_out, hh, ww = N_CH_OUT(model), engine.rows - 2, engine.cols - 2
-        w0 = model.fc0.weight.detach().view(-1, c_out, hh, ww).permute(0, 2, 3, 1).reshape(model.fc0.out_features, -1)
-        self.fcs = []
-        for w, lin, bn in ((w0, model.fc0, model.bn_fc0), (model.fc1.weight.detach(), model.fc1, model.bn_fc1)):
-            s, t = _bn_affine(bn)
-            self.fcs.append((w.to(dtype).t().contiguous(), lin.bias.detach().float().contiguous(), s, t))
+        c0 = model.conv0
+        if use_stem and dtype in (torch.bfloat16, torch.float16) and (rows, cols) in ((4, 4), (6, 6), (3, 3), (5, 5)):
+            ones = torch.ones(c0.out_channels, device=dev)
+            self.stem = _stem_tables(c0, rows, cols) + (ones, torch.zeros_like(ones))  # r0 = relu(conv0(x) + b0)
+            self.stem_out = torch.empty((cap, rows, cols, c0.out_channels), dtype=dtype, device=dev)
+        else:
+            self.conv0 = (_cl(c0.weight.detach(), dtype), c0.bias.detach().to(dtype), tuple(c0.padding))
+        self.convs = []
+        hw = (rows, cols)
+        for i in range(1, 5):
+            conv = getattr(model, f"conv{i}")
+            s, t = _bn_affine(getattr(model, f"bn{i - 1}"))
+            w32 = conv.weight.detach().float()
+            pad = tuple(conv.padding)
+            tmap = t.view(1, -1, 1, 1).expand(1, t.numel(), hw[0], hw[1]).contiguous()
+            bpos = F.conv2d(tmap, w32, None, padding=pad)[0]  # image of the shift t under this conv, [cout, H', W']
+            bias = conv.bias.detach().float()
+            z = None
+            if pad == (0, 0):
+                bias = bias + bpos[:, 0, 0]  # no padding: the same constant at every position
+            else:
+                z = bpos.to(dtype).unsqueeze(0).expand(cap, -1, -1, -1).contiguous(memory_format=torch.channels_last)
+            self.convs.append((_cl(w32 * s.view(1, -1, 1, 1), dtype), bias.to(dtype), z, pad))
+            hw = (bpos.shape[1], bpos.shape[2])
+        c_out = N_CH_OUT(model)
+        s, t = _bn_affine(model.bn4)
+        # fc0 over the NHWC flatten of conv4's output, bn4 folded in (per channel, any position)
+        w0 = model.fc0.weight.detach().float().view(-1, c_out, hw[0], hw[1])
+        b0 = model.fc0.bias.detach().float() + (w0 * t.view(1, -1, 1, 1)).sum((1, 2, 3))
+        w0 = (w0 * s.view(1, -1, 1, 1)).permute(0, 2, 3, 1).reshape(model.fc0.out_features, -1)
+        s0, t0 = _bn_affine(model.bn_fc0)
+        w1 = model.fc1.weight.detach().float()
+        b1 = model.fc1.bias.detach().float() + w1 @ t0
+        w1 = w1 * s0.view(1, -1)
+        self.fcs = [(w0.to(dtype).t().contiguous(), b0.to(dtype)), (w1.to(dtype).t().contiguous(), b1.to(dtype))]
+        s1, t1 = _bn_affine(model.bn_fc1)
         A = engine.A
         ld = (A + 1 + 7) // 8 * 8
         wh = torch.zeros((ld, model.policy_fc.in_features), dtype=torch.float32, device=dev)
         bh = torch.zeros((ld,), dtype=torch.float32, device=dev)
         wh[:A] = model.policy_fc.weight.detach(); wh[A] = model.value_fc.weight.detach()[0]
         bh[:A] = model.policy_fc.bias.detach(); bh[A] = model.value_fc.bias.detach()[0]
+        bh = bh + wh @ t1
+        wh = wh * s1.view(1, -1)
         self.wh, self.bh = wh.to(dtype).t().contiguous(), bh.to(dtype)
+        self.engine_launches = 2 if self.stem is not None else 1  # the engine's own kernels per batch: (stem,) heads
         engine.set_planes(dtype, channels_last=True)
 
     @torch.no_grad()
     def __call__(self, eng):
+        n = eng.n_rows
         if self.stem is not None:
             w01, bp, k2, s0, t0 = self.stem
-            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out[:eng.n_rows], mode=0).permute(0, 3, 1, 2)
+            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out[:n], mode=0).permute(0, 3, 1, 2)
         else:
-            x = eng.planes
-        for w, b, s, t, pad in self.convs:
-            x = F.conv2d(x, w, None, padding=pad)
-            eng.nn_epilogue(x.permute(0, 2, 3, 1), b, s, t, mode=0)
-        x = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
-        for w, b, s, t in self.fcs:
-            x = torch.mm(x, w)
-            eng.nn_epilogue(x, b, s, t, mode=0)
+            w, b, pad = self.conv0
+            x = _conv_relu(eng.planes, w, b, pad)
+        for w, b, z, pad in self.convs:
+            x = _conv_relu(x, w, b, pad) if z is None else _conv_add_relu(x, w, z[:n], b, pad)
+        x = x.permute(0, 2, 3, 1).reshape(n, -1)
+        for w, b in self.fcs:
+            x = torch._addmm_activation(b, x, w)  # relu(x @ w + b), ReLU in the GEMM epilogue
         eng.nn_heads(torch.addmm(self.bh, x, self.wh))
 
 
@@ -396,41 +443,45 @@ def N_CH_OUT(model):
 
 
 class FusedResNetZero:
-    """Inference plan for ResNetZero (nn.py:108-122): per conv one cuDNN call + one fused epilogue
-    (bias + BN + residual + ReLU); both 1x1 head convs as one conv, both head FCs as one GEMM."""
+    """Inference plan for ResNetZero (nn.py:108-122).  Here BatchNorm sits between conv and ReLU, so it folds into
+    the conv's own weights (per output channel) and bias, and every conv of the tower is ONE cuDNN kernel with its
+    epilogue fused: conv-bias-ReLU for conv1 of a block, conv-add-bias-ReLU (z = the block input) for conv2 -- two
+    kernels per residual block.  The input BatchNorm folds into the stem tables (leaf gather + conv0 + ReLU from the
+    packed leaf states, own kernel); both 1x1 head convs are one conv, both head FCs one GEMM."""
 
     def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True):
         self.engine, self.dtype = engine, dtype
         dev = engine.device
         model = model.to(dev).train(False)
-        cl = torch.channels_last
+        cap = engine.n_games * engine.max_pending
 
         def conv_pack(conv, bn):
             if isinstance(conv, nn.Sequential):
                 raise NotImplementedError("even kernel sizes are not supported by the fused plan")
             s, t = _bn_affine(bn)
-            return (conv.weight.detach().to(dtype).contiguous(memory_format=cl), conv.bias.detach().float().contiguous(), s, t,
-                    conv.padding)
+            w = conv.weight.detach().float() * s.view(-1, 1, 1, 1)
+            b = conv.bias.detach().float() * s + t
+            return _cl(w, dtype), b.to(dtype), tuple(conv.padding)
         s_in, t_in = _bn_affine(model.bn_input)
-        self.in_scale = s_in.view(1, -1, 1, 1).to(dtype)
-        self.in_shift = t_in.view(1, -1, 1, 1).to(dtype)
-        self.stem = conv_pack(model.resnet.conv0, model.resnet.bn0)
-        self.fused_stem = None
         c0 = model.resnet.conv0
-        if (use_stem and dtype in (torch.bfloat16, torch.float16) and not isinstance(c0, nn.Sequential) and c0.padding == (1, 1)
+        self.fused_stem = None
+        if (use_stem and dtype in (torch.bfloat16, torch.float16) and not isinstance(c0, nn.Sequential) and tuple(c0.padding) == (1, 1)
                 and c0.out_channels in (8, 16, 32, 64, 128, 256) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5))):
-            self.fused_stem = _stem_tables(c0, engine.rows, engine.cols, s_in, t_in) + (self.stem[2], self.stem[3])
-            self.stem_out = torch.empty((engine.n_games * engine.max_pending, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
+            self.fused_stem = _stem_tables(c0, engine.rows, engine.cols, s_in, t_in) + _bn_affine(model.resnet.bn0)
+            self.stem_out = torch.empty((cap, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
+        else:
+            self.in_scale = s_in.view(1, -1, 1, 1).to(dtype)
+            self.in_shift = t_in.view(1, -1, 1, 1).to(dtype)
+            self.stem = conv_pack(c0, model.resnet.bn0)
         self.blocks = []
         for blk in model.resnet.resblocks:
             if blk.inner_conv is not None:
                 raise NotImplementedError("inner_channels is not supported by the fused plan")
             self.blocks.append((conv_pack(blk.conv1, blk.bn1), conv_pack(blk.conv2, blk.bn2)))
         ph, vh = model.policy_head, model.value_head
-        pw, pb, ps, pt, _ = conv_pack(ph.conv0, ph.bn0)
-        vw, vb, vs, vt, _ = conv_pack(vh.conv0, vh.bn0)
-        self.head_conv = (torch.cat([pw, vw], 0).contiguous(memory_format=cl), torch.cat([pb, vb]), torch.cat([ps, vs]),
-                          torch.cat([pt, vt]))
+        pw, pb, _ = conv_pack(ph.conv0, ph.bn0)
+        vw, vb, _ = conv_pack(vh.conv0, vh.bn0)
+        self.head_conv = (torch.cat([pw, vw], 0).contiguous(memory_format=torch.channels_last), torch.cat([pb, vb]))
         cp, cv = pw.shape[0], vw.shape[0]
         hw = engine.rows * engine.cols
         A, fi = engine.A, vh.fc0.out_features
@@ -444,31 +495,25 @@ class FusedResNetZero:
         self.v_b = vh.fc1.bias.detach().to(dtype)
         self.A = A
         self.ld = (A + 1 + 7) // 8 * 8
-        self.logits = torch.zeros((engine.n_games * engine.max_pending, self.ld), dtype=dtype, device=dev)
-        self.engine_launches = 2 + 2 * len(self.blocks) + 2
+        self.logits = torch.zeros((cap, self.ld), dtype=dtype, device=dev)
+        self.engine_launches = 2 if self.fused_stem is not None else 1  # the engine's own kernels per batch: (stem,) heads
         engine.set_planes(dtype, channels_last=True)
 
     @torch.no_grad()
     def __call__(self, eng):
+        n = eng.n_rows
         if self.fused_stem is not None:
             w01, bp, k2, s0, t0 = self.fused_stem
-            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out[:eng.n_rows], mode=1).permute(0, 3, 1, 2)
+            x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out[:n], mode=1).permute(0, 3, 1, 2)
         else:
-            x = eng.planes * self.in_scale + self.in_shift
-            w, b, s, t, pad = self.stem
-            x = F.conv2d(x, w, None, padding=pad)
-            eng.nn_epilogue(x.permute(0, 2, 3, 1), b, s, t, mode=1)
-        for (w1, b1, s1, t1, p1), (w2, b2, s2, t2, p2) in self.blocks:
-            y = F.conv2d(x, w1, None, padding=p1)
-            eng.nn_epilogue(y.permute(0, 2, 3, 1), b1, s1, t1, mode=1)
-            y = F.conv2d(y, w2, None, padding=p2)
-            eng.nn_epilogue(y.permute(0, 2, 3, 1), b2, s2, t2, mode=1, res=x.permute(0, 2, 3, 1))
-            x = y
-        hw_, hb, hs, ht = self.head_conv
-        h = F.conv2d(x, hw_, None)
-        eng.nn_epilogue(h.permute(0, 2, 3, 1), hb, hs, ht, mode=1)
-        out = torch.addmm(self.head_b, h.permute(0, 2, 3, 1).reshape(h.shape[0], -1), self.head_w)
-        logits = self.logits[:eng.n_rows]
+            w, b, pad = self.stem
+            x = _conv_relu(eng.planes * self.in_scale + self.in_shift, w, b, pad)
+        for (w1, b1, p1), (w2, b2, p2) in self.blocks:
+            x = _conv_add_relu(_conv_relu(x, w1, b1, p1), w2, x, b2, p2)
+        hw_, hb = self.head_conv
+        h = _conv_relu(x, hw_, hb, (0, 0))
+        out = torch.addmm(self.head_b, h.permute(0, 2, 3, 1).reshape(n, -1), self.head_w)
+        logits = self.logits[:n]
         logits[:, :self.A] = out[:, :self.A]
         logits[:, self.A:self.A + 1] = torch.addmm(self.v_b, F.relu(out[:, self.A:]), self.v_w)
         eng.nn_heads(logits)
