@@ -179,6 +179,7 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
               alloc((void**)&ta.trees, (size_t)ta.n_trees * sizeof(TreeRec), "tree table") &&
               alloc((void**)&ta.root_prior, (size_t)ta.n_trees * A * sizeof(double), "root priors") &&
               alloc((void**)&ta.path, (size_t)max_pending * ta.n_trees * PATH_CAP * sizeof(uint32_t), "paths") &&
+              alloc((void**)&ta.path_wn, (size_t)ta.n_trees * PATH_CAP * sizeof(uint2), "path statistics") &&
               alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double2), "log/sqrt table") &&
               alloc((void**)&ta.act_tab, (size_t)A * 2 * sizeof(uint4), "action table") &&
               alloc((void**)&ta.pend, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4), "pending leaves") &&
@@ -197,6 +198,7 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     k_build_act_tab<<<1, DBAZ_MAX_ACTIONS>>>(b, const_cast<uint4*>(ta.act_tab));
     cudaMemset(ta.pend, 0, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4));
     cudaMemset(ta.ctr, 0, 8 * sizeof(int));
+    cudaMemset(ta.path_wn, 0, (size_t)ta.n_trees * PATH_CAP * sizeof(uint2));
     ta.cache_vcell = C;  // action C = horizontal edge (row 0, column C): always a padding cell
     cudaMemset(ta.path, 0, (size_t)max_pending * ta.n_trees * PATH_CAP * sizeof(uint32_t));
     // an all-empty-board root set so that the engine is usable right after create
@@ -213,6 +215,7 @@ void dbaz_engine_destroy(dbaz_engine* e) {
     cudaFree(e->ta.trees);
     cudaFree(e->ta.root_prior);
     cudaFree(e->ta.path);
+    cudaFree(e->ta.path_wn);
     cudaFree(const_cast<double2*>(e->ta.lut));
     cudaFree(const_cast<uint4*>(e->ta.act_tab));
     cudaFree(e->ta.pend);

@@ -82,7 +82,8 @@ struct TreeArgs {
     char* arena;          // n_trees * max_nodes * stride bytes
     TreeRec* trees;
     double* root_prior;   // [n_trees][A]
-    uint32_t* path;       // [n_trees][PATH_CAP]
+    uint32_t* path;       // [max_pending][n_trees][PATH_CAP]
+    uint2* path_wn;       // [n_trees][PATH_CAP]: {W, N} of each path node's own record as the selection saw them (sequential mode)
     const double2* lut;   // {c0(N) = log((N + base + 1)/base) + cpuct, sqrt(N)}, host libm
     const uint4* act_tab; // [A][2]: the two box masks each action borders (built once per engine)
     uint4* pend;          // [max_pending][n_trees][3]: pending leaf {header copy (2 x 16 B), node index, path length}
@@ -307,18 +308,27 @@ __device__ __forceinline__ void root_prior_mix(const Board& b, const TreeArgs& t
 
 // One pending simulation as the backup needs it: the leaf's header copy, node index, path and net outputs.
 // For lane 0 all of it is preloaded at kernel entry with loads whose addresses depend only on t (one round trip).
+// Path element j (node j of the path root..leaf) lives on lane j & 31, slot j >> 5; a path is at most
+// (number of real edges + 1) < 32 * APL nodes long.
 template <int APL>
 struct StepInputs {
     uint4 lh0, lh1;     // pending leaf header
     int leaf, plen;
-    uint32_t pe[PATH_CAP / 32];
+    uint32_t pe[APL];   // parent << 8 | action | to_play << 31
+    float w[APL];       // sequential mode: W and N of the node's own record (in its parent) before this simulation
+    int n[APL];
     float p[APL];
     float value;
 };
 
+// Statistics of the simulations one launch finishes for a tree, flushed to the TreeRec once (sequential mode).
+struct WaveStats {
+    int sims, term, hits, path, maxdeep;
+};
+
 // `nrow` = row of the evaluator's batch (priors / values); the engine-owned pending record and path are indexed by
 // slot and tree.  nrow < 0: k * n_trees + t (the non-compact layout).
-template <int APL>
+template <int APL, bool SEQ>
 __device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta, int t, int k, int64_t nrow,
                                              const float* __restrict__ priors, const float* __restrict__ values,
                                              StepInputs<APL>& in, int lane) {
@@ -329,7 +339,14 @@ __device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta,
     const uint4 m = pr[2];
     in.leaf = (int)m.x; in.plen = (int)m.y;
 #pragma unroll
-    for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? ta.path[row * PATH_CAP + lane + 32 * i] : 0u;
+    for (int i = 0; i < APL; ++i) {
+        in.pe[i] = ta.path[row * PATH_CAP + lane + 32 * i];
+        in.w[i] = 0.0f; in.n[i] = 0;
+        if (SEQ) {
+            const uint2 wn = ta.path_wn[(int64_t)t * PATH_CAP + lane + 32 * i];
+            in.w[i] = __uint_as_float(wn.x); in.n[i] = (int)wn.y;
+        }
+    }
 #pragma unroll
     for (int q = 0; q < APL; ++q) { int a = lane + 32 * q; in.p[q] = a < b.A ? priors[nrow * b.A + a] : 0.0f; }
     in.value = values[nrow];
@@ -398,12 +415,51 @@ __device__ __forceinline__ void cache_insert(const Board& b, const TreeArgs& ta,
 // expand + backup of one pending leaf (mcts.py:116-132 and the prior masking of 188-196).  The virtual loss was
 // subtracted by the selection that produced the path (mcts.py:109), so every path node just gets
 // W = fl32(W + fl32(v*s + 1)) and N += 1.
+// NumPy's float32 add-reduce of a[0..A) (pairwise_sum, one block of < 128 elements: eight running sums over rows of
+// eight, combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail) for a[lane + 32 k] = p[k], with shuffles:
+// lane j < 8 accumulates r[j], three butterfly steps combine them in NumPy's order (float addition commutes), lane 0
+// adds the tail; every lane returns the sum.  8 <= A <= 32 * APL.
+template <int APL>
+__device__ __forceinline__ float warp_np_sum(const float (&p)[APL], int A, int lane) {
+    const int n8 = A & ~7;
+    float r = 0.0f;
+#pragma unroll
+    for (int k = 0; k < APL; ++k)
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+            const int base = 32 * k + 8 * mm;  // row of eight: elements base..base+7 live on lanes 8*mm..8*mm+7 of slot k
+            if (base < n8) {
+                const float v = __shfl_sync(0xffffffffu, p[k], (8 * mm + lane) & 31);
+                r = (base == 0) ? v : __fadd_rn(r, v);
+            }
+        }
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        const int idx = n8 + q;
+        if (idx < A) {
+            float v = 0.0f;
+#pragma unroll
+            for (int k = 0; k < APL; ++k) if (k == (idx >> 5)) v = p[k];
+            r = __fadd_rn(r, __shfl_sync(0xffffffffu, v, idx & 31));
+        }
+    }
+    return __shfl_sync(0xffffffffu, r, 0);
+}
+
 // `src`: where in.p / in.value come from -- EV_NET (the evaluator: remembered in the eval cache if there is one),
 // EV_CACHE (a cache hit), EV_NONE (terminal leaf, no evaluation).
 enum { EV_NET = 0, EV_CACHE = 1, EV_NONE = 2 };
-template <int APL, int NW>
+// SEQ (max_pending_evals == 1): nothing reads the tree between a selection and its backup, so the selection wrote no
+// virtual loss and kept every path node's {W, N} in registers (in.w / in.n); the backup computes
+// W = fl32(fl32(W - 1) + fl32(v*s + 1)) -- the reference's two roundings -- and N + 1 from those and stores them
+// without re-reading the records; the leaf gets the +1 without the -1 (reference quirk).  Statistics go to `ws`.
+// !SEQ: the records carry the virtual loss of all selections in flight; read-modify-write.
+template <int APL, int NW, bool SEQ>
 __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArgs& ta, int t, TreeHot& T,
-                                                   const StepInputs<APL>& in, double* sh, int lane, int src) {
+                                                   const StepInputs<APL>& in, double* sh, int lane, int src, WaveStats& ws) {
     const int A = b.A;
     char* lp = node_ptr(ta, t, in.leaf);
     Hdr lh = unpack_hdr(in.lh0, in.lh1);
@@ -412,21 +468,28 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
     if (!terminal) {
         if (src == EV_NET && ta.cache) cache_insert<APL>(b, ta, lh, in, lane);
         // child_priors * valid (float32), NumPy-order sum, renormalise unless s == 1 or s <= 0
-        float* shf = reinterpret_cast<float*>(sh);
         float p[APL];
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
             int a = lane + 32 * k;
+            p[k] = 0.0f;
             if (a < A) {
                 const uint64_t ed = (NW == 1 || a < 64) ? lh.e0 : lh.e1;
                 bool legal = ((b.real[NW == 1 ? 0 : (a >> 6)] & ~ed) >> (a & 63)) & 1ull;
                 p[k] = legal ? in.p[k] : __fmul_rn(in.p[k], 0.0f);
-                shf[a] = p[k];
             }
         }
-        __syncwarp();
-        float s = np_sum<float>(shf, A);
-        __syncwarp();
+        float s;
+        if (SEQ) {
+            s = warp_np_sum<APL>(p, A, lane);
+        } else {
+            float* shf = reinterpret_cast<float*>(sh);
+#pragma unroll
+            for (int k = 0; k < APL; ++k) { int a = lane + 32 * k; if (a < A) shf[a] = p[k]; }
+            __syncwarp();
+            s = np_sum<float>(shf, A);
+            __syncwarp();
+        }
         Child* ch = node_children(lp);
         const bool renorm = (s > 0.0f && s != 1.0f);
 #pragma unroll
@@ -456,32 +519,46 @@ __device__ __forceinline__ void tree_expand_backup(const Board& b, const TreeArg
     }
     const int plen = in.plen;
 #pragma unroll
-    for (int i = 0; i < PATH_CAP / 32; ++i) {
+    for (int i = 0; i < APL; ++i) {
         const int j = lane + 32 * i;
         if (j >= plen) continue;
         const uint32_t pe = in.pe[i];
         const int tp = pe >> 31;
         const float v = (tp == lh.to_play) ? value : -value;
         const float add = __fadd_rn(v, 1.0f);
+        const bool had_vl = SEQ && j < plen - 1;  // every node the selection left behind (mcts.py:109)
         if (j == 0) {
-            T.root_W = __fadd_rn(T.root_W, add);  // only lane 0 reaches j == 0; T is written back by lane 0
+            // only lane 0 reaches j == 0; T is written back by lane 0
+            const float w0 = had_vl ? __fsub_rn(T.root_W, 1.0f) : T.root_W;
+            T.root_W = __fadd_rn(w0, add);
             T.root_N += 1;
         } else {
             const int parent = (pe & 0x7fffffffu) >> 8, act = pe & 0xffu;
             float2* cell = reinterpret_cast<float2*>(&node_children(node_ptr(ta, t, parent))[act]);
-            float2 wn = *cell;
-            wn.x = __fadd_rn(wn.x, add);
-            wn.y = __int_as_float(__float_as_int(wn.y) + 1);
+            float2 wn;
+            if (SEQ) {
+                const float w0 = had_vl ? __fsub_rn(in.w[i], 1.0f) : in.w[i];
+                wn.x = __fadd_rn(w0, add);
+                wn.y = __int_as_float(in.n[i] + 1);
+            } else {
+                wn = *cell;
+                wn.x = __fadd_rn(wn.x, add);
+                wn.y = __int_as_float(__float_as_int(wn.y) + 1);
+            }
             *cell = wn;
         }
     }
-    if (lane == 0) {
-        // tree statistics are only ever touched here: update them in place instead of carrying them in registers
+    if (SEQ) {
+        ws.sims += 1;
+        ws.term += terminal ? 1 : 0;
+        ws.hits += (src == EV_CACHE) ? 1 : 0;
+        ws.path += plen;
+        ws.maxdeep = max(ws.maxdeep, lh.depth);
+    } else if (lane == 0) {
         TreeRec* G = ta.trees + t;
         if (terminal) { G->terminal_count += 1; G->total_term += 1; }
         if (lh.depth > G->max_deepness) G->max_deepness = lh.depth;
         G->total_sims += 1;
-        if (src == EV_CACHE) G->cache_hits += 1;
         G->total_path += plen;
     }
 }
@@ -503,11 +580,13 @@ __device__ __forceinline__ int warp_argmax(double best, int best_a) {
 }
 
 // select_leaf with lazy child creation (mcts.py:105-114).  Returns the leaf kind (1 = needs evaluation,
-// 2 = terminal, 0 = node pool exhausted); leaf header / index / path length are left in `out`, the path itself in
-// `path` (global, read back by the backup).  VIRTUAL_LOSS is subtracted from every node left behind (mcts.py:109):
-// the root's own W lives in the tree record (lane 0), any other node's in its parent's child record, which the lane
-// that owned the winning action still holds from the previous level.
-template <int APL, int NW>
+// 2 = terminal, 0 = node pool exhausted); leaf header / index / path length are left in `out`.
+// !SEQ (simulations in flight): VIRTUAL_LOSS is subtracted from every node left behind (mcts.py:109) -- the root's own
+// W lives in the tree record (lane 0), any other node's in its parent's child record, which the lane that owned the
+// winning action still holds from the previous level -- and the path goes to `path` (global) for the backup.
+// SEQ (one simulation at a time): the loop stores nothing but a lazily created child; the path and each path node's
+// {W, N} stay in registers (out.pe / out.w / out.n on lane == node index) and the backup applies the virtual loss.
+template <int APL, int NW, bool SEQ>
 __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, int t, TreeHot& T,
                                            const LaneActions<APL, NW>& la, StepInputs<APL>& out, uint32_t* __restrict__ path,
                                            int lane) {
@@ -540,11 +619,16 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
         }
         const Hdr h = unpack_hdr(h0, h1);
         const bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
-        if (depth == 0 && lane == 0) path[0] = PATH_ROOT | ((uint32_t)h.to_play << 31);
+        if (depth == 0 && lane == 0) {
+            if (SEQ) out.pe[0] = PATH_ROOT | ((uint32_t)h.to_play << 31);
+            else path[0] = PATH_ROOT | ((uint32_t)h.to_play << 31);
+        }
         if (!interior) { leaf = cur; leaf_hdr = h; break; }
-        // current.total_value -= VIRTUAL_LOSS
-        if (depth == 0) { if (lane == 0) T.root_W = __fsub_rn(T.root_W, 1.0f); }
-        else if (vl_cell) *vl_cell = __fsub_rn(vl_w, 1.0f);
+        if (!SEQ) {
+            // current.total_value -= VIRTUAL_LOSS
+            if (depth == 0) { if (lane == 0) T.root_W = __fsub_rn(T.root_W, 1.0f); }
+            else if (vl_cell) *vl_cell = __fsub_rn(vl_w, 1.0f);
+        }
 
         const Mask<NW> e = hdr_edges<NW>(h);
         const double c0 = cs.x, sq = cs.y;
@@ -569,19 +653,26 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
         const int a = warp_argmax(best, best_a);  // a non-terminal node always has a legal move
         const int owner = a & 31, kk = a >> 5;
         int child = 0, childN = 0, ncl = 0;
+        uint32_t childW = 0;
         vl_cell = nullptr;
 #pragma unroll
         for (int k = 0; k < APL; ++k)
             if (k == kk) {
-                child = (int)craw[k].w; childN = (int)craw[k].y; ncl = ncl_k[k];
-                if (lane == owner) { vl_cell = &node_children(np)[a].W; vl_w = __uint_as_float(craw[k].x); }
+                child = (int)craw[k].w; childN = (int)craw[k].y; ncl = ncl_k[k]; childW = craw[k].x;
+                if (!SEQ && lane == owner) { vl_cell = &node_children(np)[a].W; vl_w = __uint_as_float(craw[k].x); }
             }
         child = __shfl_sync(0xffffffffu, child, owner);
         childN = __shfl_sync(0xffffffffu, childN, owner);
         ncl = __shfl_sync(0xffffffffu, ncl, owner);
         const int child_tp = ncl ? h.to_play : 1 - h.to_play;
         ++depth;
-        if (lane == 0) path[depth] = ((uint32_t)cur << 8) | (uint32_t)a | ((uint32_t)child_tp << 31);
+        const uint32_t pe = ((uint32_t)cur << 8) | (uint32_t)a | ((uint32_t)child_tp << 31);
+        if (SEQ) {
+            childW = __shfl_sync(0xffffffffu, childW, owner);
+#pragma unroll
+            for (int i = 0; i < APL; ++i)
+                if (i == (depth >> 5) && lane == (depth & 31)) { out.pe[i] = pe; out.w[i] = __uint_as_float(childW); out.n[i] = childN; }
+        } else if (lane == 0) path[depth] = pe;
         if (child == 0) {
             // lazily create the child (mcts.py:53-54 -> BoxesState.play, dots_boxes_game.py:91-94)
             const int idx = T.n_nodes;
@@ -650,13 +741,20 @@ k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, cons
 }
 
 // Hand a selected leaf to the evaluator: planes / packed state into batch row `row`, the engine-side pending record
-// (header copy, node index, path length) into slot `prow`.
-template <int APL, int NW>
+// (header copy, node index, path length; in sequential mode also the path registers) into slot `prow`.
+template <int APL, int NW, bool SEQ>
 __device__ __forceinline__ void emit_leaf(const Board& b, const TreeArgs& ta, const StepInputs<APL>& in, int64_t prow, int64_t row,
                                           void* __restrict__ planes, int dtype, int layout, dbaz_state* __restrict__ leaf_states,
                                           int lane) {
     const Hdr lh = unpack_hdr(in.lh0, in.lh1);
     write_planes_warp<NW>(b, hdr_edges<NW>(lh), (int)(int8_t)(lh.to_play ? lh.btc1 : lh.btc0), planes, row, dtype, layout, lane);
+    if (SEQ) {
+#pragma unroll
+        for (int i = 0; i < APL; ++i) {  // entries beyond the path length are never read
+            ta.path[prow * PATH_CAP + lane + 32 * i] = in.pe[i];
+            ta.path_wn[prow * PATH_CAP + lane + 32 * i] = make_uint2(__float_as_uint(in.w[i]), (uint32_t)in.n[i]);
+        }
+    }
     if (lane == 0) {
         uint4* pr = ta.pend + prow * 3;
         pr[0] = in.lh0; pr[1] = in.lh1; pr[2] = make_uint4((uint32_t)in.leaf, (uint32_t)in.plen, 0u, 0u);
@@ -668,89 +766,114 @@ __device__ __forceinline__ void emit_leaf(const Board& b, const TreeArgs& ta, co
     }
 }
 
-// One tree's share of a lock-step wave.  Returns true while the tree still has work (a pending leaf or simulations left).
+// max_pending_evals == 1: strictly sequential simulations.  The evaluation of the previous wave comes back, then the
+// tree runs on for as long as its simulations need no evaluator: terminal leaves (mcts.py:194-196) and leaves found
+// in the eval cache (the proxy returns those without suspending, utils/proxies.py:35-38) complete on the spot; the
+// first leaf that needs the net ends the wave.  Returns true while the tree still has work.
 template <int APL, int NW>
-__device__ __forceinline__ bool search_step_tree(const Board& b, const TreeArgs& ta, int t, int pending,
-                                                 const float* __restrict__ priors, const float* __restrict__ values,
-                                                 const double* __restrict__ noise, double coeff, void* __restrict__ planes,
-                                                 int dtype, int layout, dbaz_state* __restrict__ leaf_states,
-                                                 int8_t* __restrict__ leaf_kind, double* sh, int lane) {
+__device__ __forceinline__ bool search_step_seq(const Board& b, const TreeArgs& ta, int t,
+                                                const float* __restrict__ priors, const float* __restrict__ values,
+                                                const double* __restrict__ noise, double coeff, void* __restrict__ planes,
+                                                int dtype, int layout, dbaz_state* __restrict__ leaf_states,
+                                                int8_t* __restrict__ leaf_kind, double* sh, int lane) {
     // ---- one round trip: everything whose address depends only on t
     TreeHot T = load_hot(ta.trees + t);
-    const bool compact = ta.compact && pending == 1;
+    const bool compact = ta.compact;
     LaneActions<APL, NW> la;
     la.load(b, ta.act_tab, lane);
     StepInputs<APL> in;
-    if (!compact) load_pending<APL>(b, ta, t, 0, -1, priors, values, in, lane);
+    if (!compact) load_pending<APL, true>(b, ta, t, 0, -1, priors, values, in, lane);
 
     if (T.n_pending <= 0 && T.sims_left <= 0) {  // idle tree
-        if (leaf_kind && !compact) for (int r = lane; r < pending; r += 32) leaf_kind[(int64_t)r * ta.n_trees + t] = 0;
+        if (leaf_kind && !compact && lane == 0) leaf_kind[t] = 0;
         return false;
     }
-    if (compact) load_pending<APL>(b, ta, t, 0, T.n_pending > 0 ? T.row : 0, priors, values, in, lane);
-
-    if (pending == 1) {
-        // ---- strictly sequential simulations (max_pending_evals = 1).  The evaluation of the previous wave comes
-        // back, then the tree runs on for as long as its simulations need no evaluator: terminal leaves
-        // (mcts.py:194-196) and leaves found in the eval cache (the proxy returns those without suspending,
-        // utils/proxies.py:35-38) complete on the spot; the first leaf that needs the net ends the wave.
-        if (T.n_pending > 0) {
-            tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane, EV_NET);
-            T.n_pending = 0;
-            T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);  // lane 0 owns the authoritative TreeRec
-            __syncwarp();
-            if (T.flags & TF_PREP_PENDING) {
-                dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
-                root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
-            }
+    if (compact) load_pending<APL, true>(b, ta, t, 0, T.n_pending > 0 ? T.row : 0, priors, values, in, lane);
+    WaveStats ws = {0, 0, 0, 0, 0};
+    if (T.n_pending > 0) {
+        tree_expand_backup<APL, NW, true>(b, ta, t, T, in, sh, lane, EV_NET, ws);
+        T.n_pending = 0;
+        T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);  // lane 0 owns the authoritative TreeRec
+        __syncwarp();
+        if (T.flags & TF_PREP_PENDING) {
+            dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
+            root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
         }
-        T.flags &= ~TF_FIRST_WAVE;
-        uint32_t* path = ta.path + (int64_t)t * PATH_CAP;
-        int inline_done = 0;
-        while (T.sims_left > 0) {
-            __syncwarp();  // stores of the previous backup must be visible to this selection's loads
-            const int kind = tree_select<APL, NW>(b, ta, t, T, la, in, path, lane);
-            if (!kind) break;  // node pool exhausted
-            T.sims_left -= 1;
-            int src = EV_NONE;
-            if (kind == 1) {
-                if (ta.cache && cache_lookup<APL>(b, ta, in, lane)) src = EV_CACHE;
-                else {
-                    int64_t row = t;
-                    if (compact) {
-                        int r = 0;
-                        if (lane == 0) r = atomicAdd(&ta.ctr[0], 1);
-                        T.row = __shfl_sync(0xffffffffu, r, 0);
-                        row = T.row;
-                    }
-                    emit_leaf<APL, NW>(b, ta, in, t, row, planes, dtype, layout, leaf_states, lane);
-                    T.n_pending = 1;
-                    break;
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? path[lane + 32 * i] : 0u;
-            tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane, src);
-            T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
-            if (src == EV_CACHE && (T.flags & TF_PREP_PENDING)) {
-                __syncwarp();
-                dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
-                root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
-            }
-            if (ta.max_inline > 0 && ++inline_done >= ta.max_inline) break;
-        }
-        if (leaf_kind && !compact && lane == 0) leaf_kind[t] = (int8_t)T.n_pending;
-        if (lane == 0) store_hot(ta.trees + t, T);
-        return T.n_pending > 0 || T.sims_left > 0;
     }
+    T.flags &= ~TF_FIRST_WAVE;
+    int inline_done = 0;
+    while (T.sims_left > 0) {
+        __syncwarp();  // stores of the previous backup must be visible to this selection's loads
+        const int kind = tree_select<APL, NW, true>(b, ta, t, T, la, in, nullptr, lane);
+        if (!kind) break;  // node pool exhausted
+        T.sims_left -= 1;
+        int src = EV_NONE;
+        if (kind == 1) {
+            if (ta.cache && cache_lookup<APL>(b, ta, in, lane)) src = EV_CACHE;
+            else {
+                int64_t row = t;
+                if (compact) {
+                    int r = 0;
+                    if (lane == 0) r = atomicAdd(&ta.ctr[0], 1);
+                    T.row = __shfl_sync(0xffffffffu, r, 0);
+                    row = T.row;
+                }
+                emit_leaf<APL, NW, true>(b, ta, in, t, row, planes, dtype, layout, leaf_states, lane);
+                T.n_pending = 1;
+                break;
+            }
+        }
+        tree_expand_backup<APL, NW, true>(b, ta, t, T, in, sh, lane, src, ws);
+        T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
+        if (src == EV_CACHE && (T.flags & TF_PREP_PENDING)) {
+            __syncwarp();
+            dbaz_state rh = load_hdr(node_ptr(ta, t, 0));
+            root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
+        }
+        if (ta.max_inline > 0 && ++inline_done >= ta.max_inline) break;
+    }
+    if (lane == 0) {
+        if (leaf_kind && !compact) leaf_kind[t] = (int8_t)T.n_pending;
+        store_hot(ta.trees + t, T);
+        if (ws.sims) {  // tree statistics of the simulations this launch finished (only ever touched here)
+            TreeRec* G = ta.trees + t;
+            uint4 st = reinterpret_cast<uint4*>(G)[2];  // {deepness_correction, terminal_count, tree_size, total_term}
+            st.y += (uint32_t)ws.term; st.w += (uint32_t)ws.term;
+            reinterpret_cast<uint4*>(G)[2] = st;
+            if (ws.maxdeep > G->max_deepness) G->max_deepness = ws.maxdeep;
+            uint4 tot = reinterpret_cast<uint4*>(G)[3];  // {total_sims, cache_hits, total_path lo, hi}
+            tot.x += (uint32_t)ws.sims; tot.y += (uint32_t)ws.hits;
+            const unsigned long long tp = (((unsigned long long)tot.w << 32) | tot.z) + (unsigned long long)ws.path;
+            tot.z = (uint32_t)tp; tot.w = (uint32_t)(tp >> 32);
+            reinterpret_cast<uint4*>(G)[3] = tot;
+        }
+    }
+    return T.n_pending > 0 || T.sims_left > 0;
+}
 
-    // ---- max_pending_evals = K > 1: the reference's waves.  The evaluations of the previous wave come back:
-    // expand + backup, in selection order
+// max_pending_evals = K > 1: the reference's waves (mcts.py:228-242).  Returns true while the tree still has work.
+template <int APL, int NW>
+__device__ __forceinline__ bool search_step_waves(const Board& b, const TreeArgs& ta, int t, int pending,
+                                                  const float* __restrict__ priors, const float* __restrict__ values,
+                                                  const double* __restrict__ noise, double coeff, void* __restrict__ planes,
+                                                  int dtype, int layout, dbaz_state* __restrict__ leaf_states,
+                                                  int8_t* __restrict__ leaf_kind, double* sh, int lane) {
+    // ---- one round trip: everything whose address depends only on t
+    TreeHot T = load_hot(ta.trees + t);
+    StepInputs<APL> in;
+    load_pending<APL, false>(b, ta, t, 0, -1, priors, values, in, lane);
+    LaneActions<APL, NW> la;
+    la.load(b, ta.act_tab, lane);
+    if (T.n_pending <= 0 && T.sims_left <= 0) {  // idle tree
+        if (leaf_kind) for (int r = lane; r < pending; r += 32) leaf_kind[(int64_t)r * ta.n_trees + t] = 0;
+        return false;
+    }
+    WaveStats ws = {0, 0, 0, 0, 0};  // unused: the statistics are updated in place
+    // ---- the evaluations of the previous wave come back: expand + backup, in selection order
     const int n_back = T.n_pending;
     for (int k = 0; k < n_back; ++k) {
-        if (k > 0) { __syncwarp(); load_pending<APL>(b, ta, t, k, -1, priors, values, in, lane); }
-        tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane, EV_NONE);
+        if (k > 0) { __syncwarp(); load_pending<APL, false>(b, ta, t, k, -1, priors, values, in, lane); }
+        tree_expand_backup<APL, NW, false>(b, ta, t, T, in, sh, lane, EV_NONE, ws);
     }
     T.n_pending = 0;
     if (n_back > 0) {
@@ -774,19 +897,19 @@ __device__ __forceinline__ bool search_step_tree(const Board& b, const TreeArgs&
         __syncwarp();  // stores of the backups / previous selections must be visible to this selection's loads
         const int64_t row = (int64_t)n_out * ta.n_trees + t;
         uint32_t* path = ta.path + row * PATH_CAP;
-        const int kind = tree_select<APL, NW>(b, ta, t, T, la, in, path, lane);
+        const int kind = tree_select<APL, NW, false>(b, ta, t, T, la, in, path, lane);
         if (!kind) break;  // node pool exhausted
         T.sims_left -= 1;
         if (kind == 2) {
             // a terminal leaf never awaits the net: its simulation completes before the next one is selected
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < PATH_CAP / 32; ++i) in.pe[i] = (i == 0 || b.A > 32) ? path[lane + 32 * i] : 0u;
-            tree_expand_backup<APL, NW>(b, ta, t, T, in, sh, lane, EV_NONE);
+            for (int i = 0; i < APL; ++i) in.pe[i] = path[lane + 32 * i];
+            tree_expand_backup<APL, NW, false>(b, ta, t, T, in, sh, lane, EV_NONE, ws);
             T.root_N = __shfl_sync(0xffffffffu, T.root_N, 0);
             continue;
         }
-        emit_leaf<APL, NW>(b, ta, in, row, row, planes, dtype, layout, leaf_states, lane);
+        emit_leaf<APL, NW, false>(b, ta, in, row, row, planes, dtype, layout, leaf_states, lane);
         if (leaf_kind && lane == 0) leaf_kind[row] = 1;
         ++n_out;
     }
@@ -807,9 +930,14 @@ k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this sea
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * TREE_WARPS + warp;
     bool busy = false;
-    if (t < ta.n_trees)
-        busy = search_step_tree<APL, NW>(b, ta, t, pending, priors, values, noise, coeff, planes, dtype, layout, leaf_states,
-                                         leaf_kind, sh_all[warp], lane);
+    if (t < ta.n_trees) {
+        if (pending == 1)
+            busy = search_step_seq<APL, NW>(b, ta, t, priors, values, noise, coeff, planes, dtype, layout, leaf_states, leaf_kind,
+                                            sh_all[warp], lane);
+        else
+            busy = search_step_waves<APL, NW>(b, ta, t, pending, priors, values, noise, coeff, planes, dtype, layout, leaf_states,
+                                              leaf_kind, sh_all[warp], lane);
+    }
     // ---- wave bookkeeping: the last CTA to finish publishes {rows handed out, busy trees} and re-arms the counters
     if (lane == 0) s_busy[warp] = busy ? 1 : 0;
     __syncthreads();
