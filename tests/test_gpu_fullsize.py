@@ -47,6 +47,19 @@ def test_config1_4096_games_800_sims(mods):
     for r in runs[1:]:  # eager == graph == repeated, bit for bit
         assert torch.equal(r[0], runs[0][0]) and torch.equal(r[1], runs[0][1]) and torch.equal(r[2], runs[0][2])
     vis, W, st = runs[0]
+    # the production schedule -- eval cache, in-kernel chains, compact rows, adaptive batch ladder -- on a second engine
+    # (twice: cold table, then a table that already holds every evaluation): same counts, W and statistics, bit for bit
+    eng2 = engine.Engine((3, 3), n_games=n, max_nodes=2048, eval_cache=22)
+    for rnd in range(2):
+        eng2.reset_roots(roots)
+        eng2.run_search(sims, ev, graph_waves=8, adaptive=True)
+        W2, _, _, _ = eng2.root_children()
+        st2, _, _ = eng2.tree_stats()
+        assert torch.equal(eng2.root_visits(), vis) and torch.equal(W2, W) and torch.equal(st2, st), rnd
+        info2 = eng2.status()
+        assert info2["errors"] == 0 and info2["sims"] == n * (sims + 1)
+        assert info2["cache_hits"] > (0.3 if rnd == 0 else 0.8) * info2["sims"]
+    eng2.close()
     assert (vis.sum(1) == sims).all()                      # every simulation after the root expansion visits one child
     assert (st[:, 0] == sims + 1).all()                    # root N counts the expansion sim too
     legal = eng.valid_moves(roots)
