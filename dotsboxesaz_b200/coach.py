@@ -35,7 +35,8 @@ def selfplay(params, generation, model=None, engine=None, evaluator=None):
         if engine is None:
             n = max(1, min(int(params.self_play.get("concurrent_games", 4096) or 4096), params.self_play.num_games))
             engine = _engine.Engine(tuple(params.game.clazz.BOARD_DIM), n_games=n,
-                                    max_nodes=int(params.self_play.get("max_nodes_per_tree", 8192) or 8192))
+                                    max_nodes=int(params.self_play.get("max_nodes_per_tree", 8192) or 8192),
+                                    eval_cache=self_play.default_eval_cache(params))
         evaluator = make_evaluator(model, engine)
     df = self_play.generate_games(params.hdf_file, generation, params.nn.model_class, params.self_play.num_games, params,
                                   engine=engine, evaluator=evaluator, writer=lambda f, k, d: store.append(k, d))

@@ -474,6 +474,21 @@ def gather_samples(df, dst=0):
     return pd.concat(out).sort_index()
 
 
+def default_eval_cache(params):
+    """log2(entries) of the engine's eval cache: `params.self_play.eval_cache_log2` if given (0 = none), else about
+    2 GB worth -- the role of the reference's `nn.max_cache_size` LRU (self_play.py:226-230).  (Only searches with one
+    simulation in flight per tree use the table; generate_games builds its engine that way.)"""
+    sp = params.self_play
+    want = sp.get("eval_cache_log2", None)
+    if want is not None:
+        return int(want)
+    L, C = tuple(params.game.clazz.BOARD_DIM)
+    A = 2 * (L + 1) * (C + 1)
+    if A > 88:
+        return 0
+    return max(16, int(np.log2((2 << 30) / (16 * A))))
+
+
 def generate_games(hdf_file_name, generation, nn_class, n_games, params, n_workers=None, games_per_workers=10,
                    engine=None, evaluator=None, writer=None):
     """self_play.py:291-306.  One process per GPU (torch.distributed), `n_games` sharded by index; each rank
@@ -488,7 +503,9 @@ def generate_games(hdf_file_name, generation, nn_class, n_games, params, n_worke
     if engine is None:
         slots = max(1, min(len(mine), int(params.self_play.get("concurrent_games", 4096) or 4096)))
         engine = _engine.Engine(tuple(params.game.clazz.BOARD_DIM), n_games=slots,
-                                max_nodes=int(params.self_play.get("max_nodes_per_tree", 8192) or 8192))
+                                max_nodes=int(params.self_play.get("max_nodes_per_tree", 8192) or 8192),
+                                eval_cache=default_eval_cache(params))
+    engine.clear_eval_cache()  # cached evaluations belong to the previous generation's weights
     if evaluator is None:
         model = nn_class(params)
         if generation != 0:
