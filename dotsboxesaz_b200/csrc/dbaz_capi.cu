@@ -199,6 +199,7 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     cudaMemset(ta.pend, 0, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4));
     cudaMemset(ta.ctr, 0, 8 * sizeof(int));
     cudaMemset(ta.path_wn, 0, (size_t)ta.n_trees * PATH_CAP * sizeof(uint2));
+    ta.batch_rows = 0x7fffffff;
     ta.cache_vcell = C;  // action C = horizontal edge (row 0, column C): always a padding cell
     cudaMemset(ta.path, 0, (size_t)max_pending * ta.n_trees * PATH_CAP * sizeof(uint32_t));
     // an all-empty-board root set so that the engine is usable right after create
@@ -464,10 +465,18 @@ int dbaz_search_set_mode(dbaz_engine* e, int32_t compact, int32_t max_inline) {
     return 0;
 }
 
-int dbaz_search_wave_counts(dbaz_engine* e, int32_t* out2, uint64_t stream) {
-    if (!e || !out2) return 1;
+int dbaz_search_set_batch_rows(dbaz_engine* e, int32_t rows) {
+    if (!e) return 1;
+    if (rows < 0) return fail(e, "rows must be >= 0");
+    e->ta.batch_rows = rows > 0 ? rows : 0x7fffffff;
+    return 0;
+}
+
+int dbaz_search_wave_counts(dbaz_engine* e, int32_t* out4, uint64_t stream) {
+    if (!e || !out4) return 1;
     DeviceGuard guard(e->cfg.device);
-    DBAZ_CK(e, cudaMemcpyAsync(out2, e->ta.ctr + 4, 2 * sizeof(int), cudaMemcpyDefault, S(stream)));
+    DBAZ_CK(e, cudaMemcpyAsync(out4, e->ta.ctr + 4, 4 * sizeof(int), cudaMemcpyDefault, S(stream)));
+    DBAZ_CK(e, cudaMemsetAsync(e->ta.ctr + 6, 0, sizeof(int), S(stream)));  // the maximum restarts with every read
     return 0;
 }
 

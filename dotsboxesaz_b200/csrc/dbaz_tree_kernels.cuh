@@ -99,10 +99,12 @@ struct TreeArgs {
     uint32_t cache_mask;
     int cache_vcell;
     // lock-step bookkeeping, self-resetting (the last CTA of a launch publishes and zeroes it):
-    // ctr[0] rows handed out, ctr[1] trees still busy, ctr[2] CTAs done | ctr[4] rows of the last launch, ctr[5] busy trees
+    // ctr[0] rows asked for, ctr[1] trees still busy, ctr[2] CTAs done | ctr[4] rows asked for by the last launch,
+    // ctr[5] busy trees after it, ctr[6] largest ctr[4] since the host last read it
     int* ctr;
     int compact;          // 1: a tree's pending leaf goes to row atomicAdd(ctr[0]) instead of row == tree (pending == 1 only)
     int max_inline;       // > 0: at most this many simulations per tree and launch may finish without the net
+    int batch_rows;       // compact mode: rows the evaluator of this launch will run; a leaf beyond them waits a wave
 };
 
 __device__ __forceinline__ char* node_ptr(const TreeArgs& ta, int t, int i) {
@@ -815,8 +817,16 @@ __device__ __forceinline__ bool search_step_seq(const Board& b, const TreeArgs& 
                 if (compact) {
                     int r = 0;
                     if (lane == 0) r = atomicAdd(&ta.ctr[0], 1);
-                    T.row = __shfl_sync(0xffffffffu, r, 0);
-                    row = T.row;
+                    r = __shfl_sync(0xffffffffu, r, 0);
+                    if (r >= ta.batch_rows) {
+                        // the evaluator's batch is full: this selection is dropped and repeated in the next wave.
+                        // It stored nothing but (possibly) the new child node, which the repeat walks into, so the
+                        // repeat finds the same leaf over the same path.
+                        T.sims_left += 1;
+                        break;
+                    }
+                    T.row = r;
+                    row = r;
                 }
                 emit_leaf<APL, NW, true>(b, ta, in, t, row, planes, dtype, layout, leaf_states, lane);
                 T.n_pending = 1;
@@ -949,8 +959,10 @@ k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this sea
         __threadfence();
         if (atomicAdd(&ta.ctr[2], 1) == (int)gridDim.x - 1) {
             __threadfence();
-            ta.ctr[4] = atomicExch(&ta.ctr[0], 0);
+            const int rows = atomicExch(&ta.ctr[0], 0);
+            ta.ctr[4] = rows;
             ta.ctr[5] = atomicExch(&ta.ctr[1], 0);
+            if (rows > ta.ctr[6]) ta.ctr[6] = rows;
             ta.ctr[2] = 0;
         }
     }

@@ -76,7 +76,7 @@ class Engine:
         self.max_inline = 0
         self.set_mode(False, 4)
         self.eval_cache_log2 = 0
-        self._counts_host = torch.zeros((64, 2), dtype=torch.int32).pin_memory()
+        self._counts_host = torch.zeros((64, 4), dtype=torch.int32).pin_memory()
         self._graph_pool = None
         self.n_waves = 0             # dbaz_search_step launches (graph replays count the waves they contain)
         if eval_cache:
@@ -142,7 +142,7 @@ class Engine:
             self.compact, self.max_inline = bool(compact), int(max_inline)
 
     def wave_counts(self):
-        """(rows handed to the evaluator, busy trees) of the last step.  Synchronises the stream."""
+        """(rows the last step asked for, busy trees after it).  Synchronises the stream."""
         buf = self._counts_host[0]
         self._ck(self.lib.dbaz_search_wave_counts(self._h, C.c_void_p(buf.data_ptr()), self._stream()), launches=0)
         torch.cuda.current_stream(self.device).synchronize()
@@ -381,6 +381,7 @@ class Engine:
     # batch sizes of the adaptive loop (each one is a captured graph): n_games * k / LADDER_STEPS for k = LADDER_STEPS..1,
     # then halvings down to 64 rows
     LADDER_STEPS = 8
+    ROW_MARGIN = 1.125
 
     def _ladder(self):
         n, steps = self.n_games, max(1, int(self.LADDER_STEPS))
@@ -396,9 +397,10 @@ class Engine:
     def _run_adaptive(self, num_reads, evaluator, noise, coeff, graph_waves):
         """The wave loop with a shrinking evaluator batch.  Leaves are handed over in compact rows (set_mode), the step
         kernel publishes how many trees still have work, and the host -- one graph replay behind the device -- picks
-        the smallest captured batch that holds them (the count never grows during a search, so a stale value is
-        safe) and stops when it reads zero.  The decision for replay i+2 is taken from the count at the end of
-        replay i, which the host waits for: the schedule, and with it every evaluator batch, is reproducible."""
+        the smallest captured batch that holds the rows recent waves asked for (never more than the busy trees; a
+        batch that turns out too small only makes the surplus leaves wait a wave) and stops when no tree is busy.
+        The decision for replay i+2 is taken from the counters at the end of replay i, which the host waits for:
+        the schedule, and with it every evaluator batch, is reproducible."""
         self.pending = 1
         self.set_mode(True, self.max_inline)
         if noise is not None:
@@ -445,7 +447,10 @@ class Engine:
                 busy = int(slot0[1])
                 if busy == 0:
                     break
-                rows = min(r for r in ladder if r >= busy)
+                # the evaluator's next batch: what the waves of that replay asked for at most, plus a margin, never
+                # more than the busy trees.  Too small is safe (set_batch_rows: the surplus leaves wait a wave).
+                want = min(busy, int(int(slot0[2]) * self.ROW_MARGIN) + 32)
+                rows = min(r for r in ladder if r >= want)
 
     def _mode_key(self):
         return (self.compact, self.max_inline, self.eval_cache_log2)
@@ -461,8 +466,9 @@ class Engine:
                 evaluator(self)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
-        # the captured step kernels carry the noise pointer / coeff of begin(); bind them first
+        # the captured step kernels carry the noise pointer / coeff of begin() and the evaluator's batch; bind them first
         self._noise = noise
+        self.lib.dbaz_search_set_batch_rows(self._h, int(self._batch_rows or 0))
         self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), int(pending), _ptr(noise), float(coeff), self._stream())
         g = torch.cuda.CUDAGraph()
         n0, w0 = self.n_launches, self.n_waves
@@ -473,6 +479,7 @@ class Engine:
                 self.step()
                 evaluator(self)
         self.n_launches, self.n_waves = n0, w0  # capture enqueues nothing
+        self.lib.dbaz_search_set_batch_rows(self._h, 0)
         return g
 
     def root_visits(self):

@@ -156,10 +156,17 @@ int dbaz_search_status(dbaz_engine *e, int64_t *out8, uint64_t stream);
  * bound: a tree runs on until a leaf needs the net (the order of a tree's simulations, hence every result, is the
  * same for any setting). */
 int dbaz_search_set_mode(dbaz_engine *e, int32_t compact, int32_t max_inline);
-/* Enqueues a copy of {rows handed to the evaluator, trees that still have work} of the most recent
- * dbaz_search_step() (after dbaz_search_begin(): {0, trees with simulations to run}) on `stream` into out2 (int32[2], device or pinned host memory).  The busy-tree count never
- * grows during a search, so a stale value is a safe upper bound of the next wave's rows. */
-int dbaz_search_wave_counts(dbaz_engine *e, int32_t *out2, uint64_t stream);
+/* Compact mode: the evaluator that follows the next dbaz_search_step() calls will run rows 0..rows-1 only
+ * (0 = no limit).  A tree whose leaf would land beyond them drops that selection and repeats it in the next wave --
+ * the selection wrote nothing but a lazily created child, so the repeat finds the same leaf over the same path and
+ * no result changes; it only costs the repeat.  Lets the host size the evaluator's batch by the rows recent waves
+ * actually asked for instead of by the number of busy trees. */
+int dbaz_search_set_batch_rows(dbaz_engine *e, int32_t rows);
+/* Enqueues a copy of {rows the most recent dbaz_search_step() asked for, trees that still have work after it
+ * (after dbaz_search_begin(): trees with simulations to run), largest rows figure since the previous call, 0} on
+ * `stream` into out4 (int32[4], device or pinned host memory).  The busy-tree count never grows during a search, so
+ * a stale value is a safe upper bound of the next wave's rows. */
+int dbaz_search_wave_counts(dbaz_engine *e, int32_t *out4, uint64_t stream);
 
 /* ---- evaluation cache: the engine's form of AsyncBatchedProxy's LRU (utils/proxies.py:23-26,35-43) ----
  * A direct-mapped device table of 2^log2_entries entries (16*A bytes each) keyed by get_hash() = (edge set,
