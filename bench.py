@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--max-inline", type=int, default=4, help="bound on simulations per tree and wave finished without the net")
     ap.add_argument("--ladder-steps", type=int, default=16, help="evaluator batch sizes of the adaptive loop: games * k / steps")
     ap.add_argument("--no-ablation", action="store_true", help="skip the extra no-cache measurement")
+    ap.add_argument("--no-selfplay", action="store_true", help="skip the games/hour measurement (whole self-play games)")
+    ap.add_argument("--selfplay-nodes", type=int, default=4096, help="node pool per tree of the self-play engine (tree reuse)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="processes for the CPU baseline (0 = min(cores-1, 64))")
     ap.add_argument("--cpu-positions", type=int, default=2, help="searches per worker in the bounded CPU sample")
@@ -379,19 +381,74 @@ def main():
                 "terminal_leaf_frac": f_term, "cache_hit_frac": f_hit, "share_of_step": k_ms * waves_per_step / (ms / args.steps),
                 "sims_per_launch": sims_per_launch, "launches_per_step": waves_per_step}
         if use_cache and not args.no_ablation and world == 1:
-            # the same step with the table switched off (fixed wave loop, row == tree): what the cache buys
+            # the same step (a) with the table switched off (fixed wave loop, row == tree): what the cache buys, and
+            # (b) with the table on but every evaluator batch at full width, i.e. at the batch size of (a): the cache and
+            # the scheduling change no visit count; the production run (shrinking batches) can differ from (a) only through
+            # the library kernels the net picks at another batch size
+            step_resident()
+            vis_adaptive = visits.clone()
+            eng._ladder = lambda: [eng.n_games]
+            step_resident()
+            vis_full = visits.clone()
+            del eng._ladder
             eng.set_eval_cache(0)
 
             def step_plain():
                 eng.reset_roots(roots)
                 eng.run_search(args.sims, ev, noise=noise_dev, coeff=NOISE[1], graph_waves=args.graph_waves, pending=args.pending)
                 visits.copy_(eng.root_visits())
-            ref_visits = visits.clone()
             step_plain()
-            same = bool((ref_visits == visits).all())
             ms_plain, _ = timed(step_plain, 2)
             ablation = {"no_eval_cache_sims_per_sec": args.games * args.sims * 2 / (ms_plain / 1e3),
-                        "visit_counts_equal_to_cached_run": same}
+                        "visit_counts_equal_cached_vs_uncached_at_equal_batch_size": bool((vis_full == visits).all()),
+                        "trees_with_identical_visit_counts_production_vs_uncached": float((vis_adaptive == visits).all(1).float().mean())}
+
+    # ---- the other half of BASELINE's metric: whole self-play games per hour.  `games` games per GPU from the empty
+    # board to the end (800 sims/move, tree reuse, Dirichlet noise, temperature schedule {0: 1.0, 12: 0.02}), device-
+    # resident loop, eval cache emptied before the timed batch; the clock stops when the (planes, pi, z) samples are in
+    # host memory.
+    selfplay = None
+    node_bytes = eng.node_bytes
+    if not args.no_selfplay and args.net != "fake":
+        from dotsboxesaz_b200 import self_play as sp_mod
+        node_bytes = eng.node_bytes
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        eng_sp = engine.Engine((L, C), n_games=args.games, max_nodes=args.selfplay_nodes, device=dev, eval_cache=use_cache)
+        eng_sp.set_mode(False, args.max_inline)
+        eng_sp.LADDER_STEPS = args.ladder_steps
+        ev_sp = (FusedSimpleNN if args.net == "simple" else FusedResNetZero)(model, eng_sp, dtype=dt) if args.net_plan == "fused" \
+            else DeviceEvaluator(model, eng_sp, dtype=dt, channels_last=True)
+        sp_params = DotDict({"self_play": {"reuse_mcts_tree": True, "noise": NOISE,
+                                           "mcts": {"mcts_num_read": args.sims, "mcts_cpuct": (1.25, 19652),
+                                                    "temperature": {0: 1.0, 12: 0.02}, "max_async_searches": 1}}})
+        rows_out = [0]
+
+        def play(seed):
+            sp = sp_mod.BatchedSelfPlay(eng_sp, ev_sp, sp_params, graph_waves=args.graph_waves, adaptive=adaptive)
+            eng_sp.clear_eval_cache()
+            info = sp.play_games_device(range(args.games), seed=seed)
+            planes, pi, z, _, _ = sp.device_samples()
+            host = (planes.cpu(), pi.cpu(), z.cpu())
+            rows_out[0] = host[0].shape[0]
+            return info
+        play(1000 + rank)  # warm-up: graph captures for this engine
+        barrier()
+        t0 = time.time()
+        info = play(rank)
+        barrier()
+        sec = torch.tensor([time.time() - t0], dtype=torch.float64, device=dev)
+        tot = torch.tensor([float(info["sims"]), float(rows_out[0])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        selfplay = {"games_per_hour": args.games * world / float(sec[0]) * 3600.0, "games": args.games * world,
+                    "seconds": float(sec[0]), "sims_per_sec": float(tot[0]) / float(sec[0]), "sample_rows": int(tot[1]),
+                    "cache_hit_frac": info["cache_hits"] / max(1, info["sims"]),
+                    "terminal_leaf_frac": info["terminal_leaves"] / max(1, info["sims"]),
+                    "what": "%d concurrent games per GPU played to the end, tree reuse, temperature {0: 1.0, 12: 0.02}, samples "
+                            "copied to the host inside the timed region" % args.games}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -403,9 +460,9 @@ def main():
                            "eval_cache": ("2^%d entries, emptied at the start of every step" % use_cache) if use_cache else "off",
                            "wave_loop": "adaptive (compact rows, batch ladder)" if adaptive else "fixed", "parallelism": "games sharded by index x%d, no collective" % world,
                            "l2": "inputs larger than L2: node pool touched per step %.2f GB/GPU vs 126 MB L2" % (
-                               args.games * (args.sims + 1) * eng.node_bytes / 1e9),
+                               args.games * (args.sims + 1) * node_bytes / 1e9),
                            "graph_waves": args.graph_waves},
-                "games_per_hour_equiv": None,
+                "games_per_hour": selfplay["games_per_hour"] if selfplay else None, "selfplay": selfplay,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": max(ms_e2e, wall_e2e) / args.steps,
                         "h2d_bytes_per_step": int(roots_host.numel() * 8 + noise_pool[0].numel() * 8),
                         "d2h_bytes_per_step": int(visits_host.numel() * 4),
