@@ -217,8 +217,14 @@ async def UCT_search(root_node, num_reads, async_nn, cpuct=(1.25, 19652), max_pe
         conc[conc == 0] = 1e-60
         noise = np.random.dirichlet(conc * alpha, 1).ravel() * valid
         noise = torch.from_numpy(noise).reshape(1, -1)
-    eng.begin(int(num_reads), noise, float(coeff), pending=K)
-    await drain(int(num_reads), K)
+    num_reads = min(int(num_reads), 2_000_000_000)
+    if time_limit:
+        # a time-limited search (players.py:62-63 asks for 1e12 reads) also ends when the tree's node pool is used up:
+        # every simulation creates at most one node
+        st, _, _ = eng.tree_stats()
+        num_reads = max(0, min(num_reads, eng.max_nodes - int(st[0, 6]) - K - 1))
+    eng.begin(num_reads, noise, float(coeff), pending=K)
+    await drain(num_reads, K)
     eng.status()
     return root_node.child_number_visits
 

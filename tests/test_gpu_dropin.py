@@ -279,3 +279,36 @@ def test_elo_arena_identical_nets_split_wins(api):
     e0, e1, share = api["self_play"].compute_elo(elo, [params, params], [1, 2], (1200, 1200), models=[net, net])
     assert abs((e0 - 1200) + (e1 - 1200)) < 1e-9
     assert 0.0 <= share <= 1.0
+
+
+def test_time_limited_player(api):
+    """players.py:55-69 on the engine: `AZPlayer.serve_once` searches until the time limit and answers with the most
+    visited legal move; the deterministic fake net makes the answer checkable against a fixed-budget search."""
+    warnings.filterwarnings("ignore")
+    from dotsboxesaz_b200 import configuration, players
+    m, BoxesState = api["mcts"], api["BoxesState"]
+    BoxesState.init_static_fields(((3, 3),))
+    params = configuration.simple
+    player = players.AZPlayer(params, 0.3, None, None)
+    assert params.self_play.mcts.temperature == {0: 1e-5}
+    state = BoxesState()
+    for mv in (0, 4, 16):
+        state.play_(mv)
+    sims = [0]
+
+    async def nn(gs):
+        sims[0] += 1
+        h = gs.get_hash()[0] & 0xFFFFFFFF
+        raw = np.array([float((h * 2654435761 + i * 40503) % 1024) + 1 for i in range(32)], dtype=np.float32)
+        return raw / raw.sum(), np.array([((h % 2001) - 1000) / 1000], dtype=np.float32)
+    import time
+    t0 = time.time()
+    move = asyncio.run(player.serve_once(nn, state, 0.3))
+    dt = time.time() - t0
+    assert 0.25 < dt < 3.0 and sims[0] > 50
+    assert move is not None and state.get_valid_moves()[int(move)]
+    # a terminal position is answered with None (nothing is visited below a terminal root)
+    end = BoxesState()
+    while end.get_result() is None:
+        end.play_(int(end.get_valid_moves(as_indices=True)[0]))
+    assert asyncio.run(player.serve_once(nn, end, 0.05)) is None
