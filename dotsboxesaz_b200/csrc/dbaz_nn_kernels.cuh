@@ -301,4 +301,155 @@ k_nn_stem(const dbaz_state* __restrict__ leaves, const float* __restrict__ w01 /
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Stem on the tensor cores: the same leaf gather + first 3x3 convolution + ReLU as k_nn_stem, written as the small
+// implicit GEMM it is,  D[row][co] = relu( sum_k A[row][k] * B[k][co] ),  row = leaf * H*W + position, K = 48:
+//     k in [ 0, 18)  edge planes:   A = the edge bit under tap (plane k / 9, ky = k % 9 / 3, kx = k % 3), 0 outside the board
+//     k in [18, 27)  third plane:   A = 2 * boxes_to_close[to_play] under an in-board tap (a small integer: exact in bf16 / fp16)
+//     k in [27, 36)  in-board tap indicator (carries the shift of ResNetZero's input BatchNorm, nn.py:118)
+//     k ==  36       1 (bias: conv bias and the folded output BatchNorm shift)
+// B is folded on the host (nn.py: _stem_mma_table).  A is never materialised: a thread builds its m16n8k16 fragment
+// from the two packed edge words of its two rows through a [position][k] code table in shared memory.  One warp
+// owns a tile of 16 rows x (8 * NT) channels: 3 k-steps x NT `mma.sync` with fp32 accumulators, ReLU, then the tile goes
+// through a padded shared-memory stage so that the global stores are 16 bytes per lane over contiguous rows.
+// HBM-bound: 32 bytes in per leaf, H*W*cout*2 bytes out.
+template <typename T> struct MmaType;
+template <> struct MmaType<__nv_bfloat16> {
+    static constexpr uint32_t ONE = 0x3F80u;
+    static __device__ __forceinline__ uint32_t bits(float f) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+    static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+    static __device__ __forceinline__ uint32_t pack(float x, float y) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+};
+template <> struct MmaType<__half> {
+    static constexpr uint32_t ONE = 0x3C00u;
+    static __device__ __forceinline__ uint32_t bits(float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); }
+    static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+    static __device__ __forceinline__ uint32_t pack(float x, float y) {
+        __half2 h = __floats2half2_rn(x, y);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+};
+
+constexpr int STEM_K = 48;        // 3 k-steps of 16
+constexpr int STEM_WARPS = 4;
+
+// A-operand element for code c: 255 -> 0, < 128 -> edge bit c, 128 -> the third plane's value, 129 -> 1
+template <typename T>
+__device__ __forceinline__ uint32_t stem_a_elem(uint32_t c, uint64_t e0, uint64_t e1, uint32_t kf_bits) {
+    const uint32_t bit = (uint32_t)(((c < 64 ? e0 : e1) >> (c & 63)) & 1ull);
+    uint32_t v = bit * MmaType<T>::ONE;
+    if (c >= 128) v = (c == 128) ? kf_bits : (c == 129 ? MmaType<T>::ONE : 0u);
+    return v;
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(STEM_WARPS * 32)
+k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /*[48][cout]*/, T* __restrict__ out,
+              int n, int cout, int H, int W) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NC = 8 * NT;                       // channels per work item
+    constexpr int STAGE_ROW = NC * 2 + 16;           // bytes; +16 keeps the fragment stores conflict-free
+    const int HW = H * W;
+    const int n_chunks = cout / NC;
+    uint2* b_s = reinterpret_cast<uint2*>(smem_raw);                                   // [cout/8][3][32] fragments, 8 bytes per lane
+    unsigned char* code_s = smem_raw + (size_t)(cout / 8) * 3 * 32 * sizeof(uint2);    // [HW][48]
+    unsigned char* stage_all = code_s + ((HW * STEM_K + 15) & ~15);                    // [STEM_WARPS][16][STAGE_ROW]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+
+    // ---- B fragments: lane (g, t) of n-tile j, k-step s holds B[16s+2t][8j+g], B[16s+2t+1][8j+g] | B[16s+2t+8][..], B[16s+2t+9][..]
+    const uint16_t* w16 = reinterpret_cast<const uint16_t*>(w48);
+    for (int i = threadIdx.x; i < (cout / 8) * 3 * 32; i += blockDim.x) {
+        const int l = i & 31, js = i >> 5, s_ = js % 3, j = js / 3;
+        const int gg = l >> 2, tt = l & 3, col = 8 * j + gg, k0 = 16 * s_ + 2 * tt;
+        uint2 v;
+        v.x = (uint32_t)w16[(size_t)k0 * cout + col] | ((uint32_t)w16[(size_t)(k0 + 1) * cout + col] << 16);
+        v.y = (uint32_t)w16[(size_t)(k0 + 8) * cout + col] | ((uint32_t)w16[(size_t)(k0 + 9) * cout + col] << 16);
+        b_s[i] = v;
+    }
+    // ---- code table
+    for (int i = threadIdx.x; i < HW * STEM_K; i += blockDim.x) {
+        const int pos = i / STEM_K, k = i - pos * STEM_K;
+        const int y = pos / W, x = pos - y * W;
+        unsigned char c = 255;
+        if (k < 36) {
+            const int tap = k % 9, yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) c = (k < 18) ? (unsigned char)((k / 9) * HW + yy * W + xx) : (k < 27 ? 128 : 129);
+        } else if (k == 36) c = 129;
+        code_s[i] = c;
+    }
+    __syncthreads();
+
+    unsigned char* stage = stage_all + (size_t)warp * 16 * STAGE_ROW;
+    const long long total_rows = (long long)n * HW;
+    const long long n_tiles = (total_rows + 15) >> 4;
+    const long long n_items = n_tiles * n_chunks;
+    for (long long item = (long long)blockIdx.x * STEM_WARPS + warp; item < n_items; item += (long long)gridDim.x * STEM_WARPS) {
+        const long long tile = item / n_chunks;
+        const int chunk = (int)(item - tile * n_chunks);
+        const long long r0 = tile << 4;
+        // ---- A fragments of rows r0 + g and r0 + g + 8
+        uint32_t a[3][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long row = r0 + g + 8 * h;
+            uint64_t e0 = 0, e1 = 0;
+            uint32_t kfb = 0;
+            int pos = 0;
+            if (row < total_rows) {
+                const long long leaf = row / HW;
+                pos = (int)(row - leaf * HW);
+                const uint4 s0 = reinterpret_cast<const uint4*>(leaves + leaf)[0];
+                const uint32_t s1x = reinterpret_cast<const uint32_t*>(leaves + leaf)[4], s1y = reinterpret_cast<const uint32_t*>(leaves + leaf)[5];
+                e0 = (uint64_t)s0.x | ((uint64_t)s0.y << 32); e1 = (uint64_t)s0.z | ((uint64_t)s0.w << 32);
+                const int to_play = s1y & 0xffu;
+                const int btc = to_play ? (int)(int16_t)(s1x >> 16) : (int)(int16_t)(s1x & 0xffffu);
+                kfb = MmaType<T>::bits((float)(int)(int8_t)btc);  // np.full_like(..., dtype=np.int8)
+            }
+            const unsigned char* cr = code_s + pos * STEM_K;
+#pragma unroll
+            for (int s_ = 0; s_ < 3; ++s_) {
+                const uint32_t c01 = *reinterpret_cast<const uint16_t*>(cr + 16 * s_ + 2 * t);
+                const uint32_t c89 = *reinterpret_cast<const uint16_t*>(cr + 16 * s_ + 2 * t + 8);
+                a[s_][h] = stem_a_elem<T>(c01 & 0xffu, e0, e1, kfb) | (stem_a_elem<T>(c01 >> 8, e0, e1, kfb) << 16);
+                a[s_][2 + h] = stem_a_elem<T>(c89 & 0xffu, e0, e1, kfb) | (stem_a_elem<T>(c89 >> 8, e0, e1, kfb) << 16);
+            }
+        }
+        // ---- NT n-tiles x 3 k-steps, ReLU, into the stage
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            const uint2* bj = b_s + ((size_t)(chunk * NT + j) * 3) * 32 + lane;
+#pragma unroll
+            for (int s_ = 0; s_ < 3; ++s_) {
+                const uint2 bb = bj[s_ * 32];
+                MmaType<T>::mma(d, a[s_], bb.x, bb.y);
+            }
+            *reinterpret_cast<uint32_t*>(stage + (size_t)g * STAGE_ROW + (8 * j + 2 * t) * 2) = MmaType<T>::pack(fmaxf(d[0], 0.0f), fmaxf(d[1], 0.0f));
+            *reinterpret_cast<uint32_t*>(stage + (size_t)(g + 8) * STAGE_ROW + (8 * j + 2 * t) * 2) = MmaType<T>::pack(fmaxf(d[2], 0.0f), fmaxf(d[3], 0.0f));
+        }
+        __syncwarp();
+        // ---- 16 rows x NC channels out: 16 bytes per lane, whole rows (or row segments) contiguous
+        constexpr int CH_PER_ROW = NC * 2 / 16;  // 16-byte pieces per row segment
+        for (int q = lane; q < 16 * CH_PER_ROW; q += 32) {
+            const int rr = q / CH_PER_ROW, cc = q - rr * CH_PER_ROW;
+            const long long row = r0 + rr;
+            if (row < total_rows) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)rr * STAGE_ROW + cc * 16);
+                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(out) + ((size_t)row * cout + (size_t)chunk * NC) * 2 + cc * 16) = v;
+            }
+        }
+    }
+}
+
 }  // namespace dbaz

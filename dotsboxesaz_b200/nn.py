@@ -353,6 +353,32 @@ def _cl(w, dtype):
     return w.to(dtype).contiguous(memory_format=torch.channels_last)
 
 
+def _stem_mma_table(conv, in_scale=None, in_shift=None, out_scale=None, out_shift=None):
+    """Folded weights [48, cout] (float32) of Engine.nn_stem_mma for  relu(out_scale * (conv(in_scale * x + in_shift) + b) +
+    out_shift)  with zero padding applied AFTER the input affine (nn.py:118-119): rows 0-17 edge-plane taps, 18-26 third-plane
+    taps, 27-35 per-tap constants for in-board taps (image of in_shift), 36 bias.  See dbaz_nn_kernels.cuh."""
+    w = conv.weight.detach().float()                       # [cout, 3, 3, 3]
+    dev, cout = w.device, w.shape[0]
+    s = torch.ones(3, device=dev) if in_scale is None else in_scale.float()
+    t = torch.zeros(3, device=dev) if in_shift is None else in_shift.float()
+    so = torch.ones(cout, device=dev) if out_scale is None else out_scale.float()
+    to = torch.zeros(cout, device=dev) if out_shift is None else out_shift.float()
+    ws = w * s.view(1, 3, 1, 1)
+    tab = torch.zeros((48, cout), device=dev)
+    tab[0:18] = ws[:, :2].permute(1, 2, 3, 0).reshape(18, cout)           # [plane][ky][kx]
+    tab[18:27] = ws[:, 2].permute(1, 2, 0).reshape(9, cout)
+    tab[27:36] = (w * t.view(1, 3, 1, 1)).sum(1).permute(1, 2, 0).reshape(9, cout)
+    tab[36] = conv.bias.detach().float()
+    tab = tab * so.view(1, cout)
+    tab[36] += to
+    return tab.contiguous()
+
+
+def _stem_mma_ok(conv, engine, dtype):
+    return (dtype in (torch.bfloat16, torch.float16) and not isinstance(conv, nn.Sequential) and tuple(conv.padding) == (1, 1)
+            and conv.kernel_size == (3, 3) and conv.in_channels == 3 and conv.out_channels % 64 == 0 and conv.out_channels <= 512)
+
+
 class FusedSimpleNN:
     """Inference plan for SimpleNN (dots_boxes_nn.py:61-98), 9 kernels per batch instead of the module's ~45.
 
@@ -372,11 +398,14 @@ class FusedSimpleNN:
         model = model.to(dev).train(False)
         rows, cols = engine.rows, engine.cols
         cap = engine.n_games * engine.max_pending
-        self.stem = None
+        self.stem = self.stem_mma = None
         c0 = model.conv0
-        if use_stem and dtype in (torch.bfloat16, torch.float16) and (rows, cols) in ((4, 4), (6, 6), (3, 3), (5, 5)):
+        if use_stem and use_stem != "fma" and _stem_mma_ok(c0, engine, dtype):
+            self.stem_mma = _stem_mma_table(c0).to(dtype)                               # r0 = relu(conv0(x) + b0), tensor cores
+            self.stem_out = torch.empty((cap, rows, cols, c0.out_channels), dtype=dtype, device=dev)
+        elif use_stem and dtype in (torch.bfloat16, torch.float16) and (rows, cols) in ((4, 4), (6, 6), (3, 3), (5, 5)):
             ones = torch.ones(c0.out_channels, device=dev)
-            self.stem = _stem_tables(c0, rows, cols) + (ones, torch.zeros_like(ones))  # r0 = relu(conv0(x) + b0)
+            self.stem = _stem_tables(c0, rows, cols) + (ones, torch.zeros_like(ones))  # the same on the CUDA cores
             self.stem_out = torch.empty((cap, rows, cols, c0.out_channels), dtype=dtype, device=dev)
         else:
             self.conv0 = (_cl(c0.weight.detach(), dtype), c0.bias.detach().to(dtype), tuple(c0.padding))
@@ -418,13 +447,15 @@ class FusedSimpleNN:
         bh = bh + wh @ t1
         wh = wh * s1.view(1, -1)
         self.wh, self.bh = wh.to(dtype).t().contiguous(), bh.to(dtype)
-        self.engine_launches = 2 if self.stem is not None else 1  # the engine's own kernels per batch: (stem,) heads
+        self.engine_launches = 2 if (self.stem is not None or self.stem_mma is not None) else 1  # own kernels per batch: (stem,) heads
         engine.set_planes(dtype, channels_last=True)
 
     @torch.no_grad()
     def __call__(self, eng):
         n = eng.n_rows
-        if self.stem is not None:
+        if self.stem_mma is not None:
+            x = eng.nn_stem_mma(eng.leaf_states, self.stem_mma, self.stem_out[:n]).permute(0, 3, 1, 2)
+        elif self.stem is not None:
             w01, bp, k2, s0, t0 = self.stem
             x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out[:n], mode=0).permute(0, 3, 1, 2)
         else:
@@ -464,8 +495,12 @@ class FusedResNetZero:
             return _cl(w, dtype), b.to(dtype), tuple(conv.padding)
         s_in, t_in = _bn_affine(model.bn_input)
         c0 = model.resnet.conv0
-        self.fused_stem = None
-        if (use_stem and dtype in (torch.bfloat16, torch.float16) and not isinstance(c0, nn.Sequential) and tuple(c0.padding) == (1, 1)
+        self.fused_stem = self.stem_mma = None
+        if use_stem and use_stem != "fma" and _stem_mma_ok(c0, engine, dtype):
+            s0_, t0_ = _bn_affine(model.resnet.bn0)
+            self.stem_mma = _stem_mma_table(c0, s_in, t_in, s0_, t0_).to(dtype)  # relu(bn0(conv0(bn_input(x)))), tensor cores
+            self.stem_out = torch.empty((cap, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
+        elif (use_stem and dtype in (torch.bfloat16, torch.float16) and not isinstance(c0, nn.Sequential) and tuple(c0.padding) == (1, 1)
                 and c0.out_channels in (8, 16, 32, 64, 128, 256) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5))):
             self.fused_stem = _stem_tables(c0, engine.rows, engine.cols, s_in, t_in) + _bn_affine(model.resnet.bn0)
             self.stem_out = torch.empty((cap, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
@@ -496,13 +531,15 @@ class FusedResNetZero:
         self.A = A
         self.ld = (A + 1 + 7) // 8 * 8
         self.logits = torch.zeros((cap, self.ld), dtype=dtype, device=dev)
-        self.engine_launches = 2 if self.fused_stem is not None else 1  # the engine's own kernels per batch: (stem,) heads
+        self.engine_launches = 2 if (self.fused_stem is not None or self.stem_mma is not None) else 1  # own kernels per batch
         engine.set_planes(dtype, channels_last=True)
 
     @torch.no_grad()
     def __call__(self, eng):
         n = eng.n_rows
-        if self.fused_stem is not None:
+        if self.stem_mma is not None:
+            x = eng.nn_stem_mma(eng.leaf_states, self.stem_mma, self.stem_out[:n]).permute(0, 3, 1, 2)
+        elif self.fused_stem is not None:
             w01, bp, k2, s0, t0 = self.fused_stem
             x = eng.nn_stem(eng.leaf_states, w01, bp, k2, s0, t0, self.stem_out[:n], mode=1).permute(0, 3, 1, 2)
         else:

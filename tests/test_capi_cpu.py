@@ -100,3 +100,32 @@ def test_dataset_frame_matches_reference_columns():
     flat = df.reset_index()
     assert list(flat.columns) == cols
     assert np.array_equal(flat.to_numpy(dtype=np.float64), ref)
+
+
+def test_adaptive_ladder_and_default_cache_size():
+    """Host logic of the adaptive wave loop that needs no GPU: the batch ladder (Engine._ladder) and the default eval
+    cache size (self_play.default_eval_cache)."""
+    from dotsboxesaz_b200 import engine, self_play
+    from dotsboxesaz_b200.utils.utils import DotDict
+    e = object.__new__(engine.Engine)
+    for n, steps in ((4096, 16), (4096, 8), (192, 8), (64, 8), (100, 8), (16384, 16), (1, 8)):
+        e.n_games, e.LADDER_STEPS = n, steps
+        lad = e._ladder()
+        assert lad[0] == n and lad == sorted(set(lad), reverse=True)
+        assert all(r <= n for r in lad) and (min(lad) <= max(64, n // steps) or n <= 64)
+        assert all(r % 8 == 0 or r == n for r in lad)            # 16-byte rows for the library kernels
+        for busy in (1, n // 3, n - 1, n):                        # every busy count has a rung that holds it
+            assert min(r for r in lad if r >= busy) >= busy
+
+    class G33:
+        BOARD_DIM = (3, 3)
+
+    class G77:
+        BOARD_DIM = (7, 7)
+    p = DotDict({"self_play": {"mcts": {"max_async_searches": 64}}, "game": {"clazz": G33}})
+    k = self_play.default_eval_cache(p)
+    assert 16 <= k <= 24 and (1 << k) * 16 * 32 <= (2 << 30)      # about 2 GB of 512-byte entries
+    p.self_play.eval_cache_log2 = 0
+    assert self_play.default_eval_cache(p) == 0
+    p2 = DotDict({"self_play": {"mcts": {}}, "game": {"clazz": G77}})
+    assert self_play.default_eval_cache(p2) == 0                   # A = 128 > 88: no table

@@ -62,11 +62,14 @@ def test_fused_plans_match_torch_modules(net, board):
         assert (eng.priors.sum(1) - 1).abs().max() < 1e-3
         assert (eng.priors - p_ref).abs().max().item() < tol, (net, board, dtype, (eng.priors - p_ref).abs().max().item())
         assert (eng.values - v_ref).abs().max().item() < tol * (1 if dtype == torch.float32 else 3)
-        if dtype != torch.float32:  # the library-conv0 variant of the same plan must agree as well
-            plan2 = plan_cls(model, eng, dtype=dtype, use_stem=False)
-            eng.planes.copy_(x32.to(dtype))
-            plan2(eng)
-            assert (eng.priors - p_ref).abs().max().item() < tol
+        if dtype != torch.float32:  # the library-conv0 and the CUDA-core-stem variants of the same plan must agree as well
+            assert plan.stem_mma is not None  # the default stem is the tensor-core kernel
+            for variant in (False, "fma"):
+                plan2 = plan_cls(model, eng, dtype=dtype, use_stem=variant)
+                assert plan2.stem_mma is None
+                eng.planes.copy_(x32.to(dtype))
+                plan2(eng)
+                assert (eng.priors - p_ref).abs().max().item() < tol, variant
         # the un-fused evaluator (plain module on the same planes) must agree too
         ev = DeviceEvaluator(model, eng, dtype=dtype, channels_last=True)
         eng.planes.copy_(x32.to(dtype))
@@ -102,4 +105,47 @@ def test_epilogue_kernel_matches_torch(dtype):
             eng.nn_epilogue(y, bias, scale, shift, mode=mode, res=res.to(dt) if use_res else None)
             tol = 2 ** -7 if dtype == "bf16" else 1e-5
             assert ((y.float() - ref).abs() <= tol * (1 + ref.abs())).all(), (dtype, mode, use_res)
+    eng.close()
+
+
+@pytest.mark.parametrize("board,cout,dtype", [((3, 3), 256, "bf16"), ((5, 5), 64, "bf16"), ((2, 3), 128, "fp16"), ((4, 6), 512, "bf16")])
+def test_stem_mma_kernel_matches_conv(board, cout, dtype):
+    """dbaz_nn_stem_mma (leaf gather + conv0 + folded affines + ReLU as one tensor-core implicit GEMM from packed states)
+    against F.conv2d in fp32 on the feature planes of the same states, with the weights rounded to the storage dtype as
+    the kernel sees them.  Tolerance: fp32 accumulation order + one output rounding (2^-8 relative for bf16)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import torch.nn.functional as F
+    from dotsboxesaz_b200 import engine
+    from dotsboxesaz_b200.nn import _stem_mma_table
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    n = 777  # not a multiple of the 16-row tile
+    eng = engine.Engine(board, n_games=4, max_nodes=8)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    st = eng.new_states(n)
+    for ply in range(9):
+        legal = eng.valid_moves(st).float()
+        mv = torch.multinomial(legal + 1e-9, 1, generator=g).reshape(-1).int()
+        eng.play(st, torch.where((torch.arange(n, device="cuda") % 10 > ply) & (legal.sum(1) > 0), mv, torch.full_like(mv, -1)))
+    conv = torch.nn.Conv2d(3, cout, 3, padding=1).cuda()
+    s_in, t_in = torch.rand(3, device="cuda", generator=g) + 0.5, torch.randn(3, device="cuda", generator=g) * 0.3
+    s_o, t_o = torch.rand(cout, device="cuda", generator=g) + 0.5, torch.randn(cout, device="cuda", generator=g) * 0.2
+    tab = _stem_mma_table(conv, s_in, t_in, s_o, t_o).to(dt)
+    out = torch.empty((n, eng.rows, eng.cols, cout), dtype=dt, device="cuda")
+    eng.nn_stem_mma(st, tab, out)
+    # reference from the ROUNDED table: un-fold it into a conv over [plane0, plane1, plane2, in-board indicator]
+    t32 = tab.float()
+    w = torch.zeros((cout, 4, 3, 3), device="cuda")
+    w[:, :2] = t32[0:18].reshape(2, 3, 3, cout).permute(3, 0, 1, 2)
+    w[:, 2] = t32[18:27].reshape(3, 3, cout).permute(2, 0, 1)
+    w[:, 3] = t32[27:36].reshape(3, 3, cout).permute(2, 0, 1)
+    x = eng.features(st, torch.float32)
+    x4 = torch.cat([x, torch.ones_like(x[:, :1])], 1)
+    ref = F.relu(F.conv2d(x4, w, t32[36], padding=1)).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs()
+    assert (err <= 2 ** -7 * (1 + ref.abs())).all(), err.max().item()
+    # and the fold itself: relu(s_o * (conv(s_in * x + t_in) + b) + t_o) in fp32, up to the rounding of the table
+    with torch.no_grad():
+        full = F.relu(s_o.view(1, -1, 1, 1) * conv(x * s_in.view(1, 3, 1, 1) + t_in.view(1, 3, 1, 1)) + t_o.view(1, -1, 1, 1))
+    assert (out.float() - full.permute(0, 2, 3, 1)).abs().max().item() < 0.25
     eng.close()
