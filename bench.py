@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-ablation", action="store_true", help="skip the extra no-cache measurement")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the games/hour measurement (whole self-play games)")
     ap.add_argument("--selfplay-nodes", type=int, default=4096, help="node pool per tree of the self-play engine (tree reuse)")
+    ap.add_argument("--selfplay-games", type=int, default=32768,
+                    help="concurrent games per GPU of the games/hour measurement (the sims/s workload stays at --games)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="processes for the CPU baseline (0 = min(cores-1, 64))")
     ap.add_argument("--cpu-positions", type=int, default=2, help="searches per worker in the bounded CPU sample")
@@ -415,7 +417,8 @@ def main():
         eng.close()
         del eng
         torch.cuda.empty_cache()
-        eng_sp = engine.Engine((L, C), n_games=args.games, max_nodes=args.selfplay_nodes, device=dev, eval_cache=use_cache)
+        sp_games = args.selfplay_games
+        eng_sp = engine.Engine((L, C), n_games=sp_games, max_nodes=args.selfplay_nodes, device=dev, eval_cache=use_cache)
         eng_sp.set_mode(False, args.max_inline)
         eng_sp.LADDER_STEPS = args.ladder_steps
         ev_sp = (FusedSimpleNN if args.net == "simple" else FusedResNetZero)(model, eng_sp, dtype=dt) if args.net_plan == "fused" \
@@ -428,7 +431,7 @@ def main():
         def play(seed):
             sp = sp_mod.BatchedSelfPlay(eng_sp, ev_sp, sp_params, graph_waves=args.graph_waves, adaptive=adaptive)
             eng_sp.clear_eval_cache()
-            info = sp.play_games_device(range(args.games), seed=seed)
+            info = sp.play_games_device(range(sp_games), seed=seed)
             planes, pi, z, _, _ = sp.device_samples()
             host = (planes.cpu(), pi.cpu(), z.cpu())
             rows_out[0] = host[0].shape[0]
@@ -443,12 +446,12 @@ def main():
         if world > 1:
             dist.all_reduce(sec, op=dist.ReduceOp.MAX)
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        selfplay = {"games_per_hour": args.games * world / float(sec[0]) * 3600.0, "games": args.games * world,
+        selfplay = {"games_per_hour": sp_games * world / float(sec[0]) * 3600.0, "games": sp_games * world,
                     "seconds": float(sec[0]), "sims_per_sec": float(tot[0]) / float(sec[0]), "sample_rows": int(tot[1]),
                     "cache_hit_frac": info["cache_hits"] / max(1, info["sims"]),
                     "terminal_leaf_frac": info["terminal_leaves"] / max(1, info["sims"]),
                     "what": "%d concurrent games per GPU played to the end, tree reuse, temperature {0: 1.0, 12: 0.02}, samples "
-                            "copied to the host inside the timed region" % args.games}
+                            "copied to the host inside the timed region" % sp_games}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

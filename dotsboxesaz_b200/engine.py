@@ -78,6 +78,7 @@ class Engine:
         self.eval_cache_log2 = 0
         self._counts_host = torch.zeros((64, 4), dtype=torch.int32).pin_memory()
         self._graph_pool = None
+        self._eval_us = {}           # (id(evaluator), batch rows) -> measured microseconds per evaluator call
         self.n_waves = 0             # dbaz_search_step launches (graph replays count the waves they contain)
         if eval_cache:
             self.set_eval_cache(eval_cache)
@@ -390,6 +391,8 @@ class Engine:
     # then halvings down to 64 rows
     LADDER_STEPS = 8
     ROW_MARGIN = 1.125
+    UNDERSIZE = 0.9          # a batch may be this much smaller than the rows expected, if that serves more rows per microsecond
+    WAVE_OVERHEAD_US = 40.0  # per-wave cost that does not depend on the batch (step kernel), for the same trade-off
 
     def _ladder(self):
         n, steps = self.n_games, max(1, int(self.LADDER_STEPS))
@@ -458,7 +461,24 @@ class Engine:
                 # the evaluator's next batch: what the waves of that replay asked for at most, plus a margin, never
                 # more than the busy trees.  Too small is safe (set_batch_rows: the surplus leaves wait a wave).
                 want = min(busy, int(int(slot0[2]) * self.ROW_MARGIN) + 32)
-                rows = min(r for r in ladder if r >= want)
+                rows = self._pick_rows(ladder, want, id(evaluator))
+
+    def _pick_rows(self, ladder, want, ev_id):
+        """The batch size for waves that are expected to ask for `want` rows: among the rungs that hold at least
+        UNDERSIZE * want rows, the one that serves the most rows per microsecond of evaluator time (library GEMM/conv
+        kernels are step functions of the batch: a rung just past a tile-wave boundary costs a whole extra wave).  A rung
+        below `want` is allowed because the surplus leaves simply wait a wave (dbaz_search_set_batch_rows)."""
+        best, best_score = None, -1.0
+        for r in ladder:
+            if r < self.UNDERSIZE * want and r != ladder[0]:
+                continue
+            us = self._eval_us.get((ev_id, r))
+            if us is None:
+                return min(x for x in ladder if x >= want)
+            score = min(r, want) / (us + self.WAVE_OVERHEAD_US)
+            if score > best_score * 1.0001 or (abs(score - best_score) <= best_score * 1e-4 and r > best):
+                best, best_score = r, score
+        return best
 
     def _mode_key(self):
         return (self.compact, self.max_inline, self.eval_cache_log2)
@@ -474,14 +494,30 @@ class Engine:
                 evaluator(self)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()  # graphs never run concurrently and keep nothing alive
+        if self._batch_rows is not None:
+            # what this batch size costs on the device (a graph of 4 calls, so that no launch overhead is in the figure):
+            # the adaptive loop weighs rows served against time (see _pick_rows)
+            g0 = torch.cuda.CUDAGraph()  # private pool: dies with the graph
+            with torch.cuda.graph(g0):
+                for _ in range(4):
+                    evaluator(self)
+            g0.replay()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g0.replay()
+            g0.replay()
+            b.record()
+            torch.cuda.synchronize(self.device)
+            self._eval_us[(id(evaluator), self._batch_rows)] = a.elapsed_time(b) * 125.0
+            del g0
         # the captured step kernels carry the noise pointer / coeff of begin() and the evaluator's batch; bind them first
         self._noise = noise
         self.lib.dbaz_search_set_batch_rows(self._h, int(self._batch_rows or 0))
         self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), int(pending), _ptr(noise), float(coeff), self._stream())
         g = torch.cuda.CUDAGraph()
         n0, w0 = self.n_launches, self.n_waves
-        if self._graph_pool is None:
-            self._graph_pool = torch.cuda.graph_pool_handle()  # graphs never run concurrently and keep nothing alive
         with torch.cuda.graph(g, pool=self._graph_pool):
             for _ in range(graph_waves):
                 self.step()

@@ -47,6 +47,7 @@ torch.cuda.synchronize()
 sch = eng.last_schedule
 tot = sum(curve[r] * 8 for r, _ in sch)
 print("replays", len(sch), "net time by curve %.1f ms" % (tot / 1e3))
+print("engine's own curve:", {r: round(us, 1) for (_, r), us in sorted(eng._eval_us.items(), key=lambda kv: -kv[0][1])})
 print(" ".join("%d/%d" % (r, b) for r, b in sch))
 st = eng.status()
 print("sims", st["sims"], "hits", st["cache_hits"], "term", st["terminal_leaves"], "evals", st["sims"] - st["cache_hits"] - st["terminal_leaves"])
