@@ -57,6 +57,7 @@ SYMBOLS = {
     "dbaz_cache_clear": (C.c_int, [_P, _U64]),
     "dbaz_nn_epilogue": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _U64]),
     "dbaz_nn_stem": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I64, _U64]),
+    "dbaz_nn_stem_mma_pack": (C.c_int, [_P, _P, _P, _I32, _U64]),
     "dbaz_nn_stem_mma": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _U64]),
     "dbaz_nn_heads": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _I64, _U64]),
     "dbaz_fake_nn": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _U64]),

@@ -115,9 +115,9 @@ template <typename T, int NT>
 static int launch_stem_mma_nt(dbaz_engine* e, const dbaz_state* leaves, const T* w48, T* out, int64_t n, int cout, cudaStream_t st) {
     const int H = e->board.rows, W = e->board.cols, HW = H * W;
     const size_t smem = (size_t)(cout / 8) * 3 * 32 * sizeof(uint2) + (size_t)((HW * STEM_K + 15) & ~15) +
-                        (size_t)STEM_WARPS * 16 * (8 * NT * 2 + 16);
+                        (size_t)STEM_WARPS * 16 * (8 * (NT >= 16 ? NT / 2 : NT) * 2 + 16);
     const int64_t items = ((n * HW + 15) / 16) * (cout / (8 * NT));
-    const int resident = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
+    const int resident = (int)std::max<size_t>(1, std::min<size_t>(5, (200 * 1024) / smem));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((items + STEM_WARPS - 1) / STEM_WARPS, (int64_t)e->n_sms * resident));
     cudaError_t rc = cudaFuncSetAttribute(k_nn_stem_mma<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nn_stem_mma)", rc);
@@ -384,6 +384,15 @@ int dbaz_nn_stem(dbaz_engine* e, const dbaz_state* leaf_states, const float* w01
     if (dtype == DBAZ_BF16) return launch_stem<__nv_bfloat16>(e, leaf_states, w01, bias_pos, k2_pos, scale, shift, (__nv_bfloat16*)out, (int)n, cout, mode, S(stream));
     if (dtype == DBAZ_F16) return launch_stem<__half>(e, leaf_states, w01, bias_pos, k2_pos, scale, shift, (__half*)out, (int)n, cout, mode, S(stream));
     return fail(e, "dbaz_nn_stem: 16-bit output types only");
+}
+
+int dbaz_nn_stem_mma_pack(dbaz_engine* e, const void* w48, void* packed, int32_t cout, uint64_t stream) {
+    if (!e || !w48 || !packed) return 1;
+    if (cout < 64 || cout > 512 || cout % 64) return fail(e, "dbaz_nn_stem_mma_pack: cout must be a multiple of 64 in [64, 512]");
+    DeviceGuard guard(e->cfg.device);
+    const int n = (cout / 8) * 3 * 32;
+    k_nn_stem_mma_pack<<<blocks_for(n, 256), 256, 0, S(stream)>>>((const uint16_t*)w48, (uint2*)packed, cout);
+    return launch_ok(e, "k_nn_stem_mma_pack");
 }
 
 int dbaz_nn_stem_mma(dbaz_engine* e, const dbaz_state* leaf_states, const void* w48, void* out, int32_t cout, int32_t dtype,

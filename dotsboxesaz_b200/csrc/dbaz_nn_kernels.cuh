@@ -319,46 +319,64 @@ template <> struct MmaType<__nv_bfloat16> {
     static constexpr uint32_t ONE = 0x3F80u;
     static __device__ __forceinline__ uint32_t bits(float f) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)); }
     static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
     }
-    static __device__ __forceinline__ uint32_t pack(float x, float y) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-        return *reinterpret_cast<uint32_t*>(&h);
+    static __device__ __forceinline__ uint32_t pack_relu(float x, float y) {  // {relu(x), relu(y)} as bf16x2, one instruction
+        uint32_t r;
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+        return r;
     }
 };
 template <> struct MmaType<__half> {
     static constexpr uint32_t ONE = 0x3C00u;
     static __device__ __forceinline__ uint32_t bits(float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); }
     static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
     }
-    static __device__ __forceinline__ uint32_t pack(float x, float y) {
-        __half2 h = __floats2half2_rn(x, y);
-        return *reinterpret_cast<uint32_t*>(&h);
+    static __device__ __forceinline__ uint32_t pack_relu(float x, float y) {
+        uint32_t r;
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+        return r;
     }
 };
 
 constexpr int STEM_K = 48;        // 3 k-steps of 16
-constexpr int STEM_WARPS = 4;
+constexpr int STEM_WARPS = 8;
 
 // A-operand element for code c: 255 -> 0, < 128 -> edge bit c, 128 -> the third plane's value, 129 -> 1
 template <typename T>
-__device__ __forceinline__ uint32_t stem_a_elem(uint32_t c, uint64_t e0, uint64_t e1, uint32_t kf_bits) {
-    const uint32_t bit = (uint32_t)(((c < 64 ? e0 : e1) >> (c & 63)) & 1ull);
-    uint32_t v = bit * MmaType<T>::ONE;
-    if (c >= 128) v = (c == 128) ? kf_bits : (c == 129 ? MmaType<T>::ONE : 0u);
+__device__ __forceinline__ uint32_t stem_a_elem(uint32_t c, const uint4& e, uint32_t kf_bits) {
+    const uint32_t lo = (c & 64) ? e.z : e.x, hi = (c & 64) ? e.w : e.y;
+    const uint32_t word = (c & 32) ? hi : lo;
+    uint32_t v = ((word >> (c & 31)) & 1u) ? MmaType<T>::ONE : 0u;
+    if (c & 128) v = (c == 128) ? kf_bits : (c == 129 ? MmaType<T>::ONE : 0u);
     return v;
+}
+
+// [48][cout] weights -> mma.sync B-fragment order [cout/8][3][32 lanes][4]: lane (g, t) of n-tile j, k-step s holds
+// B[16s+2t][8j+g], B[16s+2t+1][8j+g], B[16s+2t+8][8j+g], B[16s+2t+9][8j+g]  (once per set of weights)
+__global__ void k_nn_stem_mma_pack(const uint16_t* __restrict__ w48, uint2* __restrict__ packed, int cout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (cout / 8) * 3 * 32) return;
+    const int l = i & 31, js = i >> 5, s_ = js % 3, j = js / 3;
+    const int gg = l >> 2, tt = l & 3, col = 8 * j + gg, k0 = 16 * s_ + 2 * tt;
+    uint2 v;
+    v.x = (uint32_t)w48[(size_t)k0 * cout + col] | ((uint32_t)w48[(size_t)(k0 + 1) * cout + col] << 16);
+    v.y = (uint32_t)w48[(size_t)(k0 + 8) * cout + col] | ((uint32_t)w48[(size_t)(k0 + 9) * cout + col] << 16);
+    packed[i] = v;
 }
 
 template <typename T, int NT>
 __global__ void __launch_bounds__(STEM_WARPS * 32)
-k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /*[48][cout]*/, T* __restrict__ out,
+k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /*fragment order, k_nn_stem_mma_pack*/, T* __restrict__ out,
               int n, int cout, int H, int W) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NC = 8 * NT;                       // channels per work item
-    constexpr int STAGE_ROW = NC * 2 + 16;           // bytes; +16 keeps the fragment stores conflict-free
+    constexpr int PARTS = NT >= 16 ? 2 : 1;          // the tile leaves through the stage in PARTS column parts
+    constexpr int NTP = NT / PARTS, NCP = 8 * NTP;
+    constexpr int STAGE_ROW = NCP * 2 + 16;          // bytes; +16 keeps the fragment stores conflict-free
     const int HW = H * W;
     const int n_chunks = cout / NC;
     uint2* b_s = reinterpret_cast<uint2*>(smem_raw);                                   // [cout/8][3][32] fragments, 8 bytes per lane
@@ -366,15 +384,13 @@ k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /
     unsigned char* stage_all = code_s + ((HW * STEM_K + 15) & ~15);                    // [STEM_WARPS][16][STAGE_ROW]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 
-    // ---- B fragments: lane (g, t) of n-tile j, k-step s holds B[16s+2t][8j+g], B[16s+2t+1][8j+g] | B[16s+2t+8][..], B[16s+2t+9][..]
-    const uint16_t* w16 = reinterpret_cast<const uint16_t*>(w48);
-    for (int i = threadIdx.x; i < (cout / 8) * 3 * 32; i += blockDim.x) {
-        const int l = i & 31, js = i >> 5, s_ = js % 3, j = js / 3;
-        const int gg = l >> 2, tt = l & 3, col = 8 * j + gg, k0 = 16 * s_ + 2 * tt;
-        uint2 v;
-        v.x = (uint32_t)w16[(size_t)k0 * cout + col] | ((uint32_t)w16[(size_t)(k0 + 1) * cout + col] << 16);
-        v.y = (uint32_t)w16[(size_t)(k0 + 8) * cout + col] | ((uint32_t)w16[(size_t)(k0 + 9) * cout + col] << 16);
-        b_s[i] = v;
+    // ---- B fragments, already in fragment order (k_nn_stem_mma_pack): a straight 16-byte copy
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(w48);
+        uint4* dst = reinterpret_cast<uint4*>(b_s);
+        const int n16 = (cout / 8) * 3 * 32 / 2;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     // ---- code table
     for (int i = threadIdx.x; i < HW * STEM_K; i += blockDim.x) {
@@ -390,29 +406,28 @@ k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /
     __syncthreads();
 
     unsigned char* stage = stage_all + (size_t)warp * 16 * STAGE_ROW;
-    const long long total_rows = (long long)n * HW;
-    const long long n_tiles = (total_rows + 15) >> 4;
-    const long long n_items = n_tiles * n_chunks;
-    for (long long item = (long long)blockIdx.x * STEM_WARPS + warp; item < n_items; item += (long long)gridDim.x * STEM_WARPS) {
-        const long long tile = item / n_chunks;
-        const int chunk = (int)(item - tile * n_chunks);
-        const long long r0 = tile << 4;
+    const uint32_t total_rows = (uint32_t)n * (uint32_t)HW;       // < 2^31, checked by the host
+    const uint32_t n_tiles = (total_rows + 15u) >> 4;
+    const uint32_t n_items = n_tiles * (uint32_t)n_chunks;
+    for (uint32_t item = blockIdx.x * STEM_WARPS + warp; item < n_items; item += gridDim.x * STEM_WARPS) {
+        const uint32_t tile = (n_chunks == 1) ? item : item / (uint32_t)n_chunks;
+        const int chunk = (n_chunks == 1) ? 0 : (int)(item - tile * (uint32_t)n_chunks);
+        const uint32_t r0 = tile << 4;
         // ---- A fragments of rows r0 + g and r0 + g + 8
         uint32_t a[3][4];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const long long row = r0 + g + 8 * h;
-            uint64_t e0 = 0, e1 = 0;
+            const uint32_t row = r0 + g + 8 * h;
+            uint4 e = make_uint4(0, 0, 0, 0);
             uint32_t kfb = 0;
-            int pos = 0;
+            uint32_t pos = 0;
             if (row < total_rows) {
-                const long long leaf = row / HW;
-                pos = (int)(row - leaf * HW);
-                const uint4 s0 = reinterpret_cast<const uint4*>(leaves + leaf)[0];
-                const uint32_t s1x = reinterpret_cast<const uint32_t*>(leaves + leaf)[4], s1y = reinterpret_cast<const uint32_t*>(leaves + leaf)[5];
-                e0 = (uint64_t)s0.x | ((uint64_t)s0.y << 32); e1 = (uint64_t)s0.z | ((uint64_t)s0.w << 32);
-                const int to_play = s1y & 0xffu;
-                const int btc = to_play ? (int)(int16_t)(s1x >> 16) : (int)(int16_t)(s1x & 0xffffu);
+                const uint32_t leaf = row / (uint32_t)HW;
+                pos = row - leaf * (uint32_t)HW;
+                e = reinterpret_cast<const uint4*>(leaves + leaf)[0];
+                const uint2 s1 = reinterpret_cast<const uint2*>(leaves + leaf)[2];
+                const int to_play = s1.y & 0xffu;
+                const int btc = to_play ? (int)(int16_t)(s1.x >> 16) : (int)(int16_t)(s1.x & 0xffffu);
                 kfb = MmaType<T>::bits((float)(int)(int8_t)btc);  // np.full_like(..., dtype=np.int8)
             }
             const unsigned char* cr = code_s + pos * STEM_K;
@@ -420,33 +435,47 @@ k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /
             for (int s_ = 0; s_ < 3; ++s_) {
                 const uint32_t c01 = *reinterpret_cast<const uint16_t*>(cr + 16 * s_ + 2 * t);
                 const uint32_t c89 = *reinterpret_cast<const uint16_t*>(cr + 16 * s_ + 2 * t + 8);
-                a[s_][h] = stem_a_elem<T>(c01 & 0xffu, e0, e1, kfb) | (stem_a_elem<T>(c01 >> 8, e0, e1, kfb) << 16);
-                a[s_][2 + h] = stem_a_elem<T>(c89 & 0xffu, e0, e1, kfb) | (stem_a_elem<T>(c89 >> 8, e0, e1, kfb) << 16);
+                a[s_][h] = stem_a_elem<T>(c01 & 0xffu, e, kfb) | (stem_a_elem<T>(c01 >> 8, e, kfb) << 16);
+                a[s_][2 + h] = stem_a_elem<T>(c89 & 0xffu, e, kfb) | (stem_a_elem<T>(c89 >> 8, e, kfb) << 16);
             }
         }
-        // ---- NT n-tiles x 3 k-steps, ReLU, into the stage
-        __syncwarp();
+        // ---- NT n-tiles x 3 k-steps in PARTS column parts: four independent accumulator chains in flight, ReLU, into
+        // the stage, then 16 rows x NCP channels out with 16 bytes per lane (row segments contiguous)
+        const uint2* bj = b_s + (size_t)chunk * NT * 3 * 32 + lane;
+        unsigned char* st_lo = stage + (size_t)g * STAGE_ROW + 4 * t;
+        unsigned char* st_hi = st_lo + 8 * STAGE_ROW;
+        unsigned char* obase = reinterpret_cast<unsigned char*>(out) + ((size_t)r0 * cout + (size_t)chunk * NC) * 2;
+        const uint32_t rows_here = min(16u, total_rows - r0);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            const uint2* bj = b_s + ((size_t)(chunk * NT + j) * 3) * 32 + lane;
+        for (int part = 0; part < PARTS; ++part) {
+            __syncwarp();
 #pragma unroll
-            for (int s_ = 0; s_ < 3; ++s_) {
-                const uint2 bb = bj[s_ * 32];
-                MmaType<T>::mma(d, a[s_], bb.x, bb.y);
+            for (int j0 = 0; j0 < NTP; j0 += 4) {
+                float d[4][4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) { d[jj][0] = d[jj][1] = d[jj][2] = d[jj][3] = 0.0f; }
+#pragma unroll
+                for (int s_ = 0; s_ < 3; ++s_)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const uint2 bb = bj[((part * NTP + j0 + jj) * 3 + s_) * 32];
+                        MmaType<T>::mma(d[jj], a[s_], bb.x, bb.y);
+                    }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    *reinterpret_cast<uint32_t*>(st_lo + 16 * (j0 + jj)) = MmaType<T>::pack_relu(d[jj][0], d[jj][1]);
+                    *reinterpret_cast<uint32_t*>(st_hi + 16 * (j0 + jj)) = MmaType<T>::pack_relu(d[jj][2], d[jj][3]);
+                }
             }
-            *reinterpret_cast<uint32_t*>(stage + (size_t)g * STAGE_ROW + (8 * j + 2 * t) * 2) = MmaType<T>::pack(fmaxf(d[0], 0.0f), fmaxf(d[1], 0.0f));
-            *reinterpret_cast<uint32_t*>(stage + (size_t)(g + 8) * STAGE_ROW + (8 * j + 2 * t) * 2) = MmaType<T>::pack(fmaxf(d[2], 0.0f), fmaxf(d[3], 0.0f));
-        }
-        __syncwarp();
-        // ---- 16 rows x NC channels out: 16 bytes per lane, whole rows (or row segments) contiguous
-        constexpr int CH_PER_ROW = NC * 2 / 16;  // 16-byte pieces per row segment
-        for (int q = lane; q < 16 * CH_PER_ROW; q += 32) {
-            const int rr = q / CH_PER_ROW, cc = q - rr * CH_PER_ROW;
-            const long long row = r0 + rr;
-            if (row < total_rows) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)rr * STAGE_ROW + cc * 16);
-                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(out) + ((size_t)row * cout + (size_t)chunk * NC) * 2 + cc * 16) = v;
+            __syncwarp();
+            constexpr int CH_PER_ROW = NCP * 2 / 16;  // 16-byte pieces per row segment
+#pragma unroll 4
+            for (int q = lane; q < 16 * CH_PER_ROW; q += 32) {
+                const int rr = q / CH_PER_ROW, cc = q % CH_PER_ROW;
+                if ((uint32_t)rr < rows_here) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)rr * STAGE_ROW + cc * 16);
+                    *reinterpret_cast<uint4*>(obase + (size_t)rr * cout * 2 + (size_t)part * NCP * 2 + cc * 16) = v;
+                }
             }
         }
     }

@@ -280,11 +280,18 @@ class Engine:
                                        _ptr(shift), _ptr(out), cout, _DTYPE_CODE[out.dtype], int(mode), n, self._stream()))
         return out
 
-    def nn_stem_mma(self, leaf_states, w48, out):
+    def nn_stem_mma_pack(self, w48):
+        """[48, cout] folded stem weights (bf16/fp16, contiguous) -> the fragment order nn_stem_mma() reads."""
+        w48 = w48.contiguous()
+        packed = torch.empty_like(w48)
+        self._ck(self.lib.dbaz_nn_stem_mma_pack(self._h, _ptr(w48), _ptr(packed), w48.shape[1], self._stream()))
+        return packed
+
+    def nn_stem_mma(self, leaf_states, packed, out):
         """Leaf gather + first 3x3 conv + ReLU as one tensor-core implicit GEMM from packed states (include/dbaz_b200.h).
-        w48: [48, cout] folded weights in out's dtype; out: [n, L+1, C+1, cout] contiguous (NHWC), bf16/fp16."""
+        packed: nn_stem_mma_pack(folded weights) in out's dtype; out: [n, L+1, C+1, cout] contiguous (NHWC), bf16/fp16."""
         n, cout = leaf_states.shape[0], out.shape[-1]
-        self._ck(self.lib.dbaz_nn_stem_mma(self._h, _ptr(leaf_states), _ptr(w48), _ptr(out), cout, _DTYPE_CODE[out.dtype], n,
+        self._ck(self.lib.dbaz_nn_stem_mma(self._h, _ptr(leaf_states), _ptr(packed), _ptr(out), cout, _DTYPE_CODE[out.dtype], n,
                                            self._stream()))
         return out
 

@@ -401,7 +401,7 @@ class FusedSimpleNN:
         self.stem = self.stem_mma = None
         c0 = model.conv0
         if use_stem and use_stem != "fma" and _stem_mma_ok(c0, engine, dtype):
-            self.stem_mma = _stem_mma_table(c0).to(dtype)                               # r0 = relu(conv0(x) + b0), tensor cores
+            self.stem_mma = engine.nn_stem_mma_pack(_stem_mma_table(c0).to(dtype))      # r0 = relu(conv0(x) + b0), tensor cores
             self.stem_out = torch.empty((cap, rows, cols, c0.out_channels), dtype=dtype, device=dev)
         elif use_stem and dtype in (torch.bfloat16, torch.float16) and (rows, cols) in ((4, 4), (6, 6), (3, 3), (5, 5)):
             ones = torch.ones(c0.out_channels, device=dev)
@@ -498,7 +498,7 @@ class FusedResNetZero:
         self.fused_stem = self.stem_mma = None
         if use_stem and use_stem != "fma" and _stem_mma_ok(c0, engine, dtype):
             s0_, t0_ = _bn_affine(model.resnet.bn0)
-            self.stem_mma = _stem_mma_table(c0, s_in, t_in, s0_, t0_).to(dtype)  # relu(bn0(conv0(bn_input(x)))), tensor cores
+            self.stem_mma = engine.nn_stem_mma_pack(_stem_mma_table(c0, s_in, t_in, s0_, t0_).to(dtype))  # relu(bn0(conv0(bn_input(x))))
             self.stem_out = torch.empty((cap, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
         elif (use_stem and dtype in (torch.bfloat16, torch.float16) and not isinstance(c0, nn.Sequential) and tuple(c0.padding) == (1, 1)
                 and c0.out_channels in (8, 16, 32, 64, 128, 256) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5))):

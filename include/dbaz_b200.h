@@ -197,11 +197,14 @@ int dbaz_nn_epilogue(dbaz_engine *e, void *x, const void *res, const float *bias
 int dbaz_nn_stem(dbaz_engine *e, const dbaz_state *leaf_states, const float *w01, const float *bias_pos, const float *k2_pos,
                  const float *scale, const float *shift, void *out, int32_t cout, int32_t dtype, int32_t mode, int64_t n,
                  uint64_t stream);
-/* The same stem as one tensor-core implicit GEMM (K = 48, fp32 accumulate, ReLU): w48 [48][cout] in the output dtype,
- * rows 0-17 the two edge planes' taps (plane, ky, kx), 18-26 the third plane's taps, 27-35 per-tap constants that
- * apply where the tap lies inside the board (input BatchNorm shift), 36 the bias, 37-47 zero; any output affine is
- * folded into w48 by the caller.  out [n][L+1][C+1][cout] (NHWC) bf16/fp16; cout a multiple of 64. */
-int dbaz_nn_stem_mma(dbaz_engine *e, const dbaz_state *leaf_states, const void *w48, void *out, int32_t cout, int32_t dtype,
+/* The same stem as one tensor-core implicit GEMM (K = 48, fp32 accumulate, ReLU).  Weights: w48 [48][cout] in the
+ * output dtype (16-bit), rows 0-17 the two edge planes' taps (plane, ky, kx), 18-26 the third plane's taps, 27-35
+ * per-tap constants that apply where the tap lies inside the board (input BatchNorm shift), 36 the bias, 37-47 zero;
+ * any output affine is folded into w48 by the caller.  dbaz_nn_stem_mma_pack() reorders them once into the
+ * tensor-core fragment order (`packed`: 48*cout elements), which dbaz_nn_stem_mma() takes.
+ * out [n][L+1][C+1][cout] (NHWC) bf16/fp16; cout a multiple of 64. */
+int dbaz_nn_stem_mma_pack(dbaz_engine *e, const void *w48, void *packed, int32_t cout, uint64_t stream);
+int dbaz_nn_stem_mma(dbaz_engine *e, const dbaz_state *leaf_states, const void *packed, void *out, int32_t cout, int32_t dtype,
                      int64_t n, uint64_t stream);
 /* logits [n][ld]: columns 0..A-1 policy logits, column A value pre-activation ->
  * priors float32[n][A] = softmax (exp(log_softmax)), values float32[n] = tanh. */

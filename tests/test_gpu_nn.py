@@ -132,7 +132,7 @@ def test_stem_mma_kernel_matches_conv(board, cout, dtype):
     s_o, t_o = torch.rand(cout, device="cuda", generator=g) + 0.5, torch.randn(cout, device="cuda", generator=g) * 0.2
     tab = _stem_mma_table(conv, s_in, t_in, s_o, t_o).to(dt)
     out = torch.empty((n, eng.rows, eng.cols, cout), dtype=dt, device="cuda")
-    eng.nn_stem_mma(st, tab, out)
+    eng.nn_stem_mma(st, eng.nn_stem_mma_pack(tab), out)
     # reference from the ROUNDED table: un-fold it into a conv over [plane0, plane1, plane2, in-board indicator]
     t32 = tab.float()
     w = torch.zeros((cout, 4, 3, 3), device="cuda")
