@@ -190,8 +190,12 @@ def test_batched_selfplay_matches_reference_games(api):
     games = [G for G in SELFPLAY if (G["L"], G["C"], G["num_read"], G["kind"]) == (3, 3, 100, 0)]
     assert len(games) >= 3
     eng = api["engine"].Engine((3, 3), n_games=len(games) + 1, max_nodes=2048)  # one idle slot on purpose
-    for graph_waves in (0, 8):
-        bsp = api["self_play"].BatchedSelfPlay(eng, api["engine"].FakeNetEvaluator(0), _params(api, games[0]), graph_waves=graph_waves)
+    cached = api["engine"].Engine((3, 3), n_games=len(games) + 1, max_nodes=2048, eval_cache=14)
+    # plain wave loop eager / in CUDA graphs, then the production schedule (eval cache shared by the games and kept across
+    # moves, in-kernel chains, compact rows, adaptive batches)
+    for e, graph_waves in ((eng, 0), (eng, 8), (cached, 4)):
+        bsp = api["self_play"].BatchedSelfPlay(e, api["engine"].FakeNetEvaluator(0), _params(api, games[0]), graph_waves=graph_waves)
+        assert bsp.adaptive == (e is cached)
         played = bsp.play_games([G["seed"] for G in games], seeds=[G["seed"] for G in games])
         for (idx, moves, visits, z), G in zip(played, games):
             assert moves == G["moves"] and [v.tolist() for v in visits] == G["visits"] and z == G["z"]
@@ -199,7 +203,9 @@ def test_batched_selfplay_matches_reference_games(api):
         ref_rows = np.concatenate([np.array(G["rows"], dtype=np.float64) for G in games])
         assert list(df.columns) == games[0]["columns"]
         assert np.array_equal(df.to_numpy(dtype=np.float64), ref_rows)
+    assert cached.status()["cache_hits"] > 0
     eng.close()
+    cached.close()
 
 
 def test_device_resident_selfplay_is_valid_play(api):
@@ -207,9 +213,10 @@ def test_device_resident_selfplay_is_valid_play(api):
     check what is invariant: every recorded move is legal, games end exactly when the oracle says they do, the
     result and z signs agree with the oracle, visit totals equal the simulation budget plus the reused subtree."""
     from oracle import oracle
-    eng = api["engine"].Engine((3, 3), n_games=48, max_nodes=2048)
+    eng = api["engine"].Engine((3, 3), n_games=48, max_nodes=2048, eval_cache=14)  # the production schedule
     G = SELFPLAY[0]
     bsp = api["self_play"].BatchedSelfPlay(eng, api["engine"].FakeNetEvaluator(0), _params(api, G), graph_waves=8)
+    assert bsp.adaptive
     info = bsp.play_games_device(range(48), seed=5)
     assert info["errors"] == 0
     h = bsp._device_hist
