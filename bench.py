@@ -142,7 +142,7 @@ def reference_arm(args):
                                        "thread each" % workers, "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU side
@@ -203,8 +203,30 @@ def host_noise(rs, valid_np, alpha):
     return rs.dirichlet(np.ones(A) * alpha, size=valid_np.shape[0]) * valid_np  # mcts.py:220-223
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner when NCCL_DEBUG is set
+    in the environment), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -473,7 +495,7 @@ def main():
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ablation": ablation}
         if c_rate is not None:
             line["cpu_c_oracle_1core_sims_per_sec"] = c_rate
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

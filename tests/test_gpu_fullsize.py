@@ -96,6 +96,52 @@ def test_config1_4096_games_800_sims(mods):
     eng.close()
 
 
+def test_config4_5x5_16384_games_production_schedule_equals_plain(mods):
+    """BASELINE configs[3] sizes (5x5 boxes, 16384 concurrent games; 72 actions = 3 per lane, two mask words): the
+    production schedule (eval cache, in-kernel chains, compact rows, adaptive batches) against the plain wave loop, bit for
+    bit, on 200 simulations per tree, plus conservation of visits; a spread of trees exactly against the oracle."""
+    engine, oracle = mods
+    n, sims = 16384, 200
+    ev = engine.FakeNetEvaluator(0)
+    plain = engine.Engine((5, 5), n_games=n, max_nodes=sims + 8)
+    g = torch.Generator(device=plain.device)
+    g.manual_seed(11)
+    st = plain.new_states(n)
+    depth = torch.randint(0, 25, (n,), generator=g, device=plain.device)
+    played = []
+    for ply in range(24):
+        legal = plain.valid_moves(st).float()
+        mv = torch.multinomial(legal + 1e-9, 1, generator=g).reshape(-1).int()
+        mv = torch.where(depth > ply, mv, torch.full_like(mv, -1))
+        played.append(mv.cpu().numpy())
+        plain.play(st, mv)
+    plain.reset_roots(st)
+    plain.run_search(sims, ev, graph_waves=8)
+    vis, (W, P, _, U), (stats, rW, q) = plain.root_visits(), plain.root_children(), plain.tree_stats()
+    plain.close()
+    eng = engine.Engine((5, 5), n_games=n, max_nodes=sims + 8, eval_cache=20)
+    eng.reset_roots(st)
+    eng.run_search(sims, ev, graph_waves=8, adaptive=True)
+    W2, P2, _, U2 = eng.root_children()
+    stats2, rW2, q2 = eng.tree_stats()
+    assert torch.equal(eng.root_visits(), vis) and torch.equal(W2, W) and torch.equal(P2, P) and torch.equal(U2, U)
+    assert torch.equal(stats2, stats) and torch.equal(rW2, rW) and torch.equal(q2, q)
+    info = eng.status()
+    assert info["errors"] == 0 and info["cache_hits"] > 0
+    terminal_root = stats[:, 5] == 1
+    assert (vis.sum(1)[~terminal_root] == sims).all() and (vis.sum(1)[terminal_root] == 0).all()
+    eng.close()
+    vis_np = vis.cpu().numpy()
+    for t in range(0, n, 1489):
+        og = oracle.OracleGame(5, 5)
+        for mv in played:
+            if mv[t] >= 0:
+                og.play_(int(mv[t]))
+        if og.result() is not None:
+            continue
+        assert np.array_equal(oracle.OracleTree(5, 5, og.s).search(sims), vis_np[t]), t
+
+
 def test_config3_million_random_playouts(mods):
     """BASELINE configs[2]: 5x5, 2^20 concurrent games, random legal moves to terminal."""
     engine, _ = mods
