@@ -522,6 +522,12 @@ class Engine:
         # the captured step kernels carry the noise pointer / coeff of begin() and the evaluator's batch; bind them first
         self._noise = noise
         self.lib.dbaz_search_set_batch_rows(self._h, int(self._batch_rows or 0))
+        # small batches are the tail of a search, where a wave costs the evaluator's latency floor whatever it serves:
+        # longer in-kernel chains there save whole waves (any bound gives the same results)
+        inline = self.max_inline
+        if self._batch_rows is not None and inline > 0:
+            inline *= 4 if self._batch_rows * 16 <= self.n_games else (2 if self._batch_rows * 4 <= self.n_games else 1)
+        self.lib.dbaz_search_set_mode(self._h, 1 if self.compact else 0, int(inline))
         self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), int(pending), _ptr(noise), float(coeff), self._stream())
         g = torch.cuda.CUDAGraph()
         n0, w0 = self.n_launches, self.n_waves
@@ -531,6 +537,7 @@ class Engine:
                 evaluator(self)
         self.n_launches, self.n_waves = n0, w0  # capture enqueues nothing
         self.lib.dbaz_search_set_batch_rows(self._h, 0)
+        self.lib.dbaz_search_set_mode(self._h, 1 if self.compact else 0, int(self.max_inline))
         return g
 
     def root_visits(self):
