@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-ablation", action="store_true", help="skip the extra no-cache measurement")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the games/hour measurement (whole self-play games)")
     ap.add_argument("--selfplay-nodes", type=int, default=4096, help="node pool per tree of the self-play engine (tree reuse)")
+    ap.add_argument("--selfplay-mode", default="async", choices=["async", "lockstep"],
+                    help="async: every game at its own pace (BatchedSelfPlay.play_games_async); lockstep: all games move together")
     ap.add_argument("--selfplay-games", type=int, default=32768,
                     help="concurrent games per GPU of the games/hour measurement (the sims/s workload stays at --games)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -451,9 +453,10 @@ def main():
         rows_out = [0]
 
         def play(seed):
-            sp = sp_mod.BatchedSelfPlay(eng_sp, ev_sp, sp_params, graph_waves=args.graph_waves, adaptive=adaptive)
+            use_async = args.selfplay_mode == "async" and adaptive
+            sp = sp_mod.BatchedSelfPlay(eng_sp, ev_sp, sp_params, graph_waves=16 if use_async else args.graph_waves, adaptive=adaptive)
             eng_sp.clear_eval_cache()
-            info = sp.play_games_device(range(sp_games), seed=seed)
+            info = (sp.play_games_async if use_async else sp.play_games_device)(range(sp_games), seed=seed)
             planes, pi, z, _, _ = sp.device_samples()
             host = (planes.cpu(), pi.cpu(), z.cpu())
             rows_out[0] = host[0].shape[0]
@@ -472,8 +475,9 @@ def main():
                     "seconds": float(sec[0]), "sims_per_sec": float(tot[0]) / float(sec[0]), "sample_rows": int(tot[1]),
                     "cache_hit_frac": info["cache_hits"] / max(1, info["sims"]),
                     "terminal_leaf_frac": info["terminal_leaves"] / max(1, info["sims"]),
-                    "what": "%d concurrent games per GPU played to the end, tree reuse, temperature {0: 1.0, 12: 0.02}, samples "
-                            "copied to the host inside the timed region" % sp_games}
+                    "what": "%d concurrent games per GPU played to the end (%s), tree reuse, temperature {0: 1.0, 12: 0.02}, "
+                            "samples copied to the host inside the timed region"
+                            % (sp_games, "every game at its own pace" if args.selfplay_mode == "async" and adaptive else "all games move by move")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

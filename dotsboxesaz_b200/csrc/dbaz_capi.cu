@@ -484,6 +484,13 @@ int dbaz_search_tree_stats(dbaz_engine* e, int32_t* stats8, float* root_W, float
     return launch_ok(e, "k_tree_stats");
 }
 
+int dbaz_search_tree_busy(dbaz_engine* e, int8_t* out, uint64_t stream) {
+    if (!e || !out) return 1;
+    DeviceGuard guard(e->cfg.device);
+    k_tree_busy<<<blocks_for(e->ta.n_trees, 256), 256, 0, S(stream)>>>(e->ta, out);
+    return launch_ok(e, "k_tree_busy");
+}
+
 int dbaz_search_root_states(dbaz_engine* e, dbaz_state* out, uint64_t stream) {
     if (!e || !out) return 1;
     DeviceGuard guard(e->cfg.device);

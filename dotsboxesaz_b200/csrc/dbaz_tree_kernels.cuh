@@ -712,8 +712,9 @@ k_search_begin(Board b, TreeArgs ta, const int32_t* __restrict__ num_reads, cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * TREE_WARPS + warp;
     if (t >= ta.n_trees) return;
-    TreeHot T = load_hot(ta.trees + t);
     const int nr = num_reads[t];
+    if (nr == -3) return;  // this tree is in the middle of a search of its own: leave it alone
+    TreeHot T = load_hot(ta.trees + t);
     T.n_pending = 0;
     T.flags &= ~TF_FIRST_WAVE;
     if (nr == -2) {
@@ -1188,6 +1189,14 @@ __global__ void k_tree_stats(TreeArgs ta, int32_t* __restrict__ stats8, float* _
     }
     if (root_W) root_W[t] = T.root_W;
     if (q) q[t] = __fdiv_rn(T.root_W, (float)(1 + T.root_N));  // mcts.py:35
+}
+
+// 1 while a tree has simulations left or a leaf waiting for the evaluator
+__global__ void k_tree_busy(TreeArgs ta, int8_t* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ta.n_trees) return;
+    const TreeHot T = load_hot(ta.trees + t);
+    out[t] = (T.sims_left > 0 || T.n_pending > 0) ? 1 : 0;
 }
 
 __global__ void k_root_states(TreeArgs ta, dbaz_state* __restrict__ out) {

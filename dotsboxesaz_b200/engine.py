@@ -428,18 +428,7 @@ class Engine:
             noise = self._noise_buf
         ladder = self._ladder()
         per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
-        key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, 1, self._mode_key(), "ladder", self.LADDER_STEPS)
-        if key not in self._graphs:
-            # every batch size is captured up front: capturing re-binds the search head and idles all trees
-            graphs = {}
-            for rows in ladder:
-                self._batch_rows = rows
-                try:
-                    graphs[rows] = self._capture(evaluator, graph_waves, noise, coeff, 1)
-                finally:
-                    self._batch_rows = None
-            self._graphs[key] = (graphs, evaluator)
-        graphs = self._graphs[key][0]
+        graphs = self._ladder_graphs(evaluator, graph_waves, noise, coeff)
         self.begin(num_reads, noise, coeff, 1)
         stream = torch.cuda.current_stream(self.device)
         events = []
@@ -469,6 +458,21 @@ class Engine:
                 # more than the busy trees.  Too small is safe (set_batch_rows: the surplus leaves wait a wave).
                 want = min(busy, int(int(slot0[2]) * self.ROW_MARGIN) + 32)
                 rows = self._pick_rows(ladder, want, id(evaluator))
+
+    def _ladder_graphs(self, evaluator, graph_waves, noise, coeff):
+        """{batch rows: CUDA graph of `graph_waves` [step -> evaluator] waves} for every rung of the ladder (compact mode).
+        Every batch size is captured up front: capturing re-binds the search head and idles all trees."""
+        key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, 1, self._mode_key(), "ladder", self.LADDER_STEPS)
+        if key not in self._graphs:
+            graphs = {}
+            for rows in self._ladder():
+                self._batch_rows = rows
+                try:
+                    graphs[rows] = self._capture(evaluator, graph_waves, noise, coeff, 1)
+                finally:
+                    self._batch_rows = None
+            self._graphs[key] = (graphs, evaluator)
+        return self._graphs[key][0]
 
     def _pick_rows(self, ladder, want, ev_id):
         """The batch size for waves that are expected to ask for `want` rows: among the rungs that hold at least
@@ -569,6 +573,12 @@ class Engine:
         out = torch.empty((self.n_games, 4), dtype=torch.int64, device=self.device)
         self._ck(self.lib.dbaz_search_root_states(self._h, _ptr(out), self._stream()))
         return out
+
+    def tree_busy(self):
+        """bool[n_games]: the tree's search is still running."""
+        out = torch.empty((self.n_games,), dtype=torch.int8, device=self.device)
+        self._ck(self.lib.dbaz_search_tree_busy(self._h, _ptr(out), self._stream()))
+        return out.bool()
 
     def advance_roots(self, moves, reuse=True):
         """init_mcts_tree (mcts.py:163-180) for every tree; moves int32[n_games], -1 = keep."""

@@ -14,6 +14,8 @@ generate_games   self_play.py:291-306 re-targeted: games are sharded by index ov
 import logging
 import math
 
+import ctypes as C
+
 import numpy as np
 import pandas as pd
 import torch
@@ -277,6 +279,146 @@ class BatchedSelfPlay:
         self.total_sims = info["sims"]
         self._device_hist = dict(states=hist_states, visits=hist_visits, active=hist_active, moves=hist_moves, stats=hist_stats,
                                  q=hist_q, final=final, result=res, games_idxs=games_idxs, with_features=with_features)
+        return info
+
+    def play_games_async(self, games_idxs, seed=0, start_states=None, with_features=True):
+        """play_games_device() without the per-move lock-step: every game runs at its own pace.  A tree whose search has
+        finished samples its move, re-roots and starts its next search at the next check (once per CUDA-graph replay)
+        while the other trees are still searching, so no game waits for the slowest search of each move -- the batch
+        takes as long as its slowest GAME, not as the sum of the slowest searches.  Same algorithm, hyper-parameters,
+        per-game move sequence semantics and sample layout as play_games_device(); the moves are drawn from the same kind
+        of device generator but in a different order, so individual games differ between the two.
+
+        Needs the adaptive wave loop's machinery (compact rows, batch ladder, one simulation in flight per tree)."""
+        eng, sp = self.eng, self.params.self_play
+        n, A, dev = eng.n_games, eng.A, eng.device
+        games_idxs = list(games_idxs)
+        assert len(games_idxs) == n, "play_games_async fills every engine slot"
+        assert self.pending == 1 and self.graph_waves > 0, "play_games_async needs max_pending_evals == 1 and CUDA graphs"
+        alpha, coeff = sp.noise
+        num_read = sp.mcts.mcts_num_read
+        temp_sched = sp.mcts.temperature
+        n_edges = eng.L * (eng.C + 1) + eng.C * (eng.L + 1)
+        eng.set_cpuct(sp.mcts.mcts_cpuct)
+        eng.reset_roots(start_states)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(seed))
+        roots0 = eng.root_states()
+        played0 = int((~eng.valid_moves(roots0[:1])).sum().item()) - (A - n_edges)  # plies already on the board
+        n_moves = n_edges - played0
+        if alpha > 0:
+            g = torch._standard_gamma(torch.full((n_moves, n, A), float(alpha), dtype=torch.float64, device=dev), generator=gen)
+            noise_all = g / g.sum(-1, keepdim=True)
+        else:
+            noise_all = torch.zeros((n_moves, n, A), dtype=torch.float64, device=dev)
+        # per move index: temperature (piecewise constant schedule); per number of legal moves: simulation budget
+        temps, t_cur = [], None
+        for m in range(n_moves):
+            t_cur = float(temp_sched[m]) if m in temp_sched else t_cur
+            temps.append(t_cur)
+        inv_temp = 1.0 / torch.tensor(temps, dtype=torch.float64, device=dev)
+        reads_by_k = torch.tensor([_n_searches(k, num_read) if k > 0 else 0 for k in range(n_edges + 1)], dtype=torch.int32, device=dev)
+        ar = torch.arange(n, device=dev)
+        h_states = torch.zeros((n_moves, n, 4), dtype=torch.int64, device=dev)
+        h_visits = torch.zeros((n_moves, n, A), dtype=torch.int32, device=dev)
+        h_active = torch.zeros((n_moves, n), dtype=torch.bool, device=dev)
+        h_moves = torch.full((n_moves, n), -1, dtype=torch.int32, device=dev)
+        h_stats = torch.zeros((n_moves, n, 8), dtype=torch.int32, device=dev)
+        h_q = torch.zeros((n_moves, n), dtype=torch.float32, device=dev)
+        move_idx = torch.zeros((n,), dtype=torch.int64, device=dev)
+        leave = torch.full((n,), -3, dtype=torch.int32, device=dev)
+
+        eng.pending = 1
+        eng.set_mode(True, eng.max_inline)
+        if eng._noise_buf is None:
+            eng._noise_buf = torch.zeros((n, A), dtype=torch.float64, device=dev)
+        noise_buf = eng._noise_buf
+        noise_arg = noise_buf if alpha > 0 else None  # alpha <= 0: the reference mixes the scalar 0.0 in (float32 arithmetic)
+        graphs = eng._ladder_graphs(self.ev, self.graph_waves, noise_arg, coeff)
+        ladder = eng._ladder()
+        per_wave = 1 + int(getattr(self.ev, "engine_launches", 0))
+
+        def start(restart):
+            """Begin the next search of the trees in `restart` (bool[n]); the others are left alone."""
+            roots = eng.root_states()
+            valid = eng.valid_moves(roots)
+            over = eng.result(roots) != RESULT_NONE
+            restart = restart & ~over
+            mi = move_idx.clamp(max=n_moves - 1)
+            noise_buf.copy_(torch.where(restart.unsqueeze(1), noise_all[mi, ar] * valid, noise_buf))
+            reads = torch.where(restart, reads_by_k[valid.sum(1)], leave)
+            eng.begin(reads, noise_arg, coeff, 1)
+            return restart
+
+        searching = start(torch.ones((n,), dtype=torch.bool, device=dev)).clone()
+        u_all = torch.rand((n_moves, n), dtype=torch.float64, device=dev, generator=gen)  # one uniform per (move, game): the draw of the move
+        left_dev = torch.zeros((), dtype=torch.int32, device=dev)
+
+        def finish():
+            """Trees whose search has finished: record the sample, draw the move, re-root, start the next search.
+            Static shapes and in-place state only, so the whole phase is one CUDA graph."""
+            done = searching & ~eng.tree_busy()
+            roots = eng.root_states()
+            vis = eng.root_visits()
+            stats, _rw, q = eng.tree_stats()
+            v = vis.double()
+            mi = move_idx.clamp(max=n_moves - 1)
+            probs = (v / v.max(1, keepdim=True).values.clamp_min(1.0)) ** inv_temp[mi].unsqueeze(1)
+            cdf = probs.cumsum(1)
+            target = u_all[mi, ar].unsqueeze(1) * cdf[:, -1:]
+            moves = (cdf <= target).sum(1).clamp(max=A - 1).int()   # first action whose cumulative weight exceeds the target
+            moves = torch.where(done, moves, torch.full_like(moves, -1))
+            d1 = done.unsqueeze(1)
+            h_states[mi, ar] = torch.where(d1, roots, h_states[mi, ar])
+            h_visits[mi, ar] = torch.where(d1, vis, h_visits[mi, ar])
+            h_stats[mi, ar] = torch.where(d1, stats, h_stats[mi, ar])
+            h_q[mi, ar] = torch.where(done, q, h_q[mi, ar])
+            h_moves[mi, ar] = torch.where(done, moves, h_moves[mi, ar])
+            h_active[mi, ar] = h_active[mi, ar] | done
+            eng.advance_roots(moves, reuse=bool(sp.reuse_mcts_tree))
+            move_idx.add_(done.long())
+            searching.copy_((searching & ~done) | start(done))
+            left_dev.copy_(searching.sum().to(torch.int32))
+
+        torch.cuda.synchronize(dev)
+        fgraph = torch.cuda.CUDAGraph()
+        l0 = eng.n_launches
+        with torch.cuda.graph(fgraph):
+            finish()
+        finish_launches = eng.n_launches - l0  # engine kernels inside the finish graph
+        eng.n_launches = l0
+        stream = torch.cuda.current_stream(dev)
+        counts = torch.zeros((64, 4), dtype=torch.int32).pin_memory()
+        left = torch.zeros((64,), dtype=torch.int32).pin_memory()
+        events = []
+        rows, i = ladder[0], 0
+        while True:
+            graphs[rows].replay()
+            eng.n_launches += self.graph_waves * per_wave + finish_launches
+            eng.n_waves += self.graph_waves
+            slot = counts[i % 64]
+            eng.lib.dbaz_search_wave_counts(eng._h, C.c_void_p(slot.data_ptr()), eng._stream())
+            fgraph.replay()
+            left[i % 64].copy_(left_dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            events.append((ev, slot, left[i % 64]))
+            i += 1
+            if len(events) >= 2:
+                ev0, slot0, left0 = events.pop(0)
+                ev0.synchronize()
+                if int(left0) == 0:
+                    break
+                want = min(n, int(int(slot0[2]) * eng.ROW_MARGIN) + 32)
+                rows = eng._pick_rows(ladder, want, id(self.ev))
+        del fgraph
+        final = eng.root_states()
+        res = eng.result(final)
+        info = eng.status()
+        self.total_sims = info["sims"]
+        self._device_hist = dict(states=list(h_states.unbind(0)), visits=list(h_visits.unbind(0)), active=list(h_active.unbind(0)),
+                                 moves=list(h_moves.unbind(0)), stats=list(h_stats.unbind(0)), q=list(h_q.unbind(0)), final=final,
+                                 result=res, games_idxs=games_idxs, with_features=with_features)
         return info
 
     def device_samples(self):

@@ -106,7 +106,8 @@ int dbaz_game_random_rollout(dbaz_engine *e, dbaz_state *states, uint64_t seed, 
 /* create_root_uct_node (mcts.py:156-160) for all n_games trees */
 int dbaz_search_reset_roots(dbaz_engine *e, const dbaz_state *root_states, uint64_t stream);
 /* Head of UCT_search (mcts.py:205-229).  num_reads int32[n_games] (-1 = tree idle this search;
- * -2 = only the initial _search() of an unexpanded root, without the prior mix).
+ * -2 = only the initial _search() of an unexpanded root, without the prior mix; -3 = leave the tree alone: it is in
+ * the middle of a search started by an earlier call -- trees need not start their searches together).
  * pending = max_pending_evals (1 <= pending <= cfg.max_pending): simulations in flight per tree.  With 1 the
  * simulations of a tree are strictly sequential; with K the engine reproduces the waves the reference's event loop
  * runs when the net suspends each _search() once (mcts.py:228-242): K select_leaf()s back to back, each leaving its
@@ -140,6 +141,8 @@ int dbaz_search_root_children(dbaz_engine *e, float *W, double *priors, int32_t 
  * n_nodes, error}; root_W float32[n]; q float32[n] (TreeRoot.get_tree_stats, mcts.py:33-36) */
 int dbaz_search_tree_stats(dbaz_engine *e, int32_t *stats8, float *root_W, float *q, uint64_t stream);
 int dbaz_search_root_states(dbaz_engine *e, dbaz_state *out, uint64_t stream);
+/* int8[n_games]: 1 while the tree's search is running (simulations left or a leaf waiting for the evaluator) */
+int dbaz_search_tree_busy(dbaz_engine *e, int8_t *out, uint64_t stream);
 /* init_mcts_tree (mcts.py:163-180): moves int32[n_games], -1 = leave that tree alone.  With
  * reuse != 0 the chosen child's subtree is kept (compacted in place), else a fresh root. */
 int dbaz_search_advance_roots(dbaz_engine *e, const int32_t *moves, int32_t reuse, uint64_t stream);

@@ -208,16 +208,18 @@ def test_batched_selfplay_matches_reference_games(api):
     cached.close()
 
 
-def test_device_resident_selfplay_is_valid_play(api):
-    """play_games_device(): no host sync between moves, device RNG.  Not seed-identical to the reference, so
-    check what is invariant: every recorded move is legal, games end exactly when the oracle says they do, the
-    result and z signs agree with the oracle, visit totals equal the simulation budget plus the reused subtree."""
+@pytest.mark.parametrize("mode", ["device", "async"])
+def test_device_resident_selfplay_is_valid_play(api, mode):
+    """play_games_device() (no host sync between moves, device RNG) and play_games_async() (every game at its own pace).
+    Not seed-identical to the reference, so check what is invariant: every recorded move is legal, games end exactly when
+    the oracle says they do, the result and z signs agree with the oracle, visit totals equal the simulation budget plus
+    the reused subtree, and the recorded features are those of the position searched."""
     from oracle import oracle
     eng = api["engine"].Engine((3, 3), n_games=48, max_nodes=2048, eval_cache=14)  # the production schedule
     G = SELFPLAY[0]
-    bsp = api["self_play"].BatchedSelfPlay(eng, api["engine"].FakeNetEvaluator(0), _params(api, G), graph_waves=8)
+    bsp = api["self_play"].BatchedSelfPlay(eng, api["engine"].FakeNetEvaluator(0), _params(api, G), graph_waves=8 if mode == "device" else 2)
     assert bsp.adaptive
-    info = bsp.play_games_device(range(48), seed=5)
+    info = (bsp.play_games_device if mode == "device" else bsp.play_games_async)(range(48), seed=5)
     assert info["errors"] == 0
     h = bsp._device_hist
     moves = torch.stack(h["moves"]).cpu().numpy()       # [n_moves, n]

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--sims", type=int, default=800)
     ap.add_argument("--net", default="simple", choices=["simple", "resnet", "fake"])
     ap.add_argument("--max-nodes", type=int, default=8192)
-    ap.add_argument("--mode", default="device", choices=["device", "host"])
+    ap.add_argument("--mode", default="device", choices=["device", "async", "host"])
     ap.add_argument("--repeats", type=int, default=1)
     ap.add_argument("--pending", type=int, default=1, help="max_async_searches (simulations in flight per tree)")
     ap.add_argument("--no-warmup", action="store_true")
@@ -57,8 +57,8 @@ def main():
         w0 = eng.n_waves
         torch.cuda.synchronize()
         t0 = time.time()
-        if args.mode == "device":
-            info = sp.play_games_device(range(args.games), seed=rep)
+        if args.mode in ("device", "async"):
+            info = (sp.play_games_device if args.mode == "device" else sp.play_games_async)(range(args.games), seed=rep)
             rows = sp.device_samples()[0].shape[0]
         else:
             sp.play_games(range(args.games), seeds=range(rep * args.games, (rep + 1) * args.games))
