@@ -451,15 +451,21 @@ def main():
                                            "mcts": {"mcts_num_read": args.sims, "mcts_cpuct": (1.25, 19652),
                                                     "temperature": {0: 1.0, 12: 0.02}, "max_async_searches": 1}}})
         rows_out = [0]
+        pinned = {}
 
         def play(seed):
             use_async = args.selfplay_mode == "async" and adaptive
             sp = sp_mod.BatchedSelfPlay(eng_sp, ev_sp, sp_params, graph_waves=16 if use_async else args.graph_waves, adaptive=adaptive)
             eng_sp.clear_eval_cache()
             info = (sp.play_games_async if use_async else sp.play_games_device)(range(sp_games), seed=seed)
-            planes, pi, z, _, _ = sp.device_samples()
-            host = (planes.cpu(), pi.cpu(), z.cpu())
-            rows_out[0] = host[0].shape[0]
+            outs = sp.device_samples()[:3]  # (planes int16, pi float64, z float32), still on the device
+            for k, t in enumerate(outs):     # ... into pinned host buffers (allocated by the warm-up call, reused)
+                need = t.numel()
+                if k not in pinned or pinned[k].numel() < need:
+                    pinned[k] = torch.empty((int(need * 1.1),), dtype=t.dtype).pin_memory()
+                pinned[k][:need].copy_(t.reshape(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            rows_out[0] = outs[0].shape[0]
             return info
         play(1000 + rank)  # warm-up: graph captures for this engine
         barrier()

@@ -426,6 +426,7 @@ int dbaz_nn_heads(dbaz_engine* e, const void* logits, int32_t ld, int32_t dtype,
 int dbaz_search_reset_roots(dbaz_engine* e, const dbaz_state* root_states, uint64_t stream) {
     if (!e || !root_states) return 1;
     DeviceGuard guard(e->cfg.device);
+    DBAZ_CK(e, cudaMemsetAsync(e->ta.ctr + 7, 0, sizeof(int), S(stream)));
     k_reset_roots<<<blocks_for(e->ta.n_trees, 128), 128, 0, S(stream)>>>(e->board, e->ta, root_states);
     e->noise = nullptr; e->coeff = 0.0;
     return launch_ok(e, "k_reset_roots");

@@ -100,7 +100,7 @@ struct TreeArgs {
     int cache_vcell;
     // lock-step bookkeeping, self-resetting (the last CTA of a launch publishes and zeroes it):
     // ctr[0] rows asked for, ctr[1] trees still busy, ctr[2] CTAs done | ctr[4] rows asked for by the last launch,
-    // ctr[5] busy trees after it, ctr[6] largest ctr[4] since the host last read it
+    // ctr[5] busy trees after it, ctr[6] largest ctr[4] since the host last read it, ctr[7] largest node pool use seen by a re-root
     int* ctr;
     int compact;          // 1: a tree's pending leaf goes to row atomicAdd(ctr[0]) instead of row == tree (pending == 1 only)
     int max_inline;       // > 0: at most this many simulations per tree and launch may finish without the net
@@ -1036,6 +1036,7 @@ k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reu
     const int child = root_interior ? s_entry.child : 0;
     const int nb_visits = root_interior ? s_entry.N : 0;
     const int n = T.n_nodes;
+    if (tid == 0) atomicMax(&ta.ctr[7], n);  // high-water mark of the node pools (dbaz_search_status)
 
     if (child == 0 || !reuse) {
         if (tid == 0) {
@@ -1216,7 +1217,7 @@ __global__ void k_status(TreeArgs ta, unsigned long long* __restrict__ out4) {
     atomicAdd(&out4[1], (unsigned long long)T.total_sims);
     atomicAdd(&out4[5], (unsigned long long)T.cache_hits);
     atomicAdd(&out4[2], T.total_path);
-    atomicMax(&out4[3], (unsigned long long)T.n_nodes);
+    atomicMax(&out4[3], (unsigned long long)max(T.n_nodes, t == 0 ? ta.ctr[7] : 0));
     atomicAdd(&out4[4], (unsigned long long)T.total_term);
 }
 

@@ -396,7 +396,7 @@ class Engine:
 
     # batch sizes of the adaptive loop (each one is a captured graph): n_games * k / LADDER_STEPS for k = LADDER_STEPS..1,
     # then halvings down to 64 rows
-    LADDER_STEPS = 8
+    LADDER_STEPS = 16
     ROW_MARGIN = 1.125
     UNDERSIZE = 0.9          # a batch may be this much smaller than the rows expected, if that serves more rows per microsecond
     WAVE_OVERHEAD_US = 40.0  # per-wave cost that does not depend on the batch (step kernel), for the same trade-off

@@ -147,7 +147,7 @@ int dbaz_search_tree_busy(dbaz_engine *e, int8_t *out, uint64_t stream);
  * reuse != 0 the chosen child's subtree is kept (compacted in place), else a fresh root. */
 int dbaz_search_advance_roots(dbaz_engine *e, const int32_t *moves, int32_t reuse, uint64_t stream);
 /* Synchronises `stream`.  out int64[8] = {trees with an error flag, total sims, total path nodes,
- * max n_nodes, terminal leaves, eval-cache hits, 0, 0} (totals since reset_roots).  Returns non-zero (and sets
+ * largest node-pool use of any tree (now or at a re-root), terminal leaves, eval-cache hits, 0, 0} (since reset_roots).  Returns non-zero (and sets
  * last_error) if any tree faulted. */
 int dbaz_search_status(dbaz_engine *e, int64_t *out8, uint64_t stream);
 
