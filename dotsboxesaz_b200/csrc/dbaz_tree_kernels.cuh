@@ -8,6 +8,12 @@
 // behind, a terminal leaf backed up on the spot, then the K expand/backup pairs in the same order;
 // mcts.py:228-242).  Parallelism comes from the thousands of trees.
 //
+// What a launch of k_search_step does for one tree (max_pending_evals = 1, search_step_seq): back up the leaf the
+// evaluator answered, then run simulations back to back for as long as they need no evaluator -- terminal leaves and
+// leaves found in the eval cache (the reference's LRU of net outputs, utils/proxies.py:35-43) finish on the spot --
+// until a leaf needs the net: it goes to the next free row of the evaluator's batch (or waits a wave if the batch is
+// full).  The selection loop stores nothing but lazily created children; path and statistics stay in registers.
+//
 // HBM layout per tree t (arena[t] = max_nodes fixed-stride nodes):
 //   node i : [ dbaz_state header 32 B | Child rec[A] 16 B each ]      stride = 32 + 16*A
 // A node's own N/W live in its parent's Child record (as in mcts.py:67-89); the root's live
@@ -15,10 +21,11 @@
 // kept subtree to the front of the arena), so Child.child == 0 means "not created".
 //
 // Reference behaviour restated (paths relative to the reference root):
-//   mcts.py:91-103   children_ucb_score / best_child  -> select_level()
+//   mcts.py:91-103   children_ucb_score / best_child  -> ucb_score() + warp_argmax() inside tree_select()
 //   mcts.py:105-114  select_leaf                      -> tree_select()
 //   mcts.py:116-132  expand / backup                  -> tree_expand_backup()
-//   mcts.py:184-199  _search                          -> k_search_step
+//   mcts.py:184-199  _search                          -> search_step_seq() / search_step_waves() in k_search_step
+//   utils/proxies.py:35-43  LRU of net outputs        -> cache_lookup() / cache_insert()
 //   mcts.py:205-229  UCT_search head (root prior mix) -> root_prior_mix()
 //   mcts.py:163-180  init_mcts_tree                   -> k_advance_roots
 #pragma once
