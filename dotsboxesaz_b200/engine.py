@@ -440,8 +440,8 @@ class Engine:
         while True:
             self.last_schedule.append((rows, busy))
             graphs[rows].replay()
-            self.n_launches += graph_waves * per_wave
-            self.n_waves += graph_waves
+            self.n_launches += self._rung_waves(rows, graph_waves) * per_wave
+            self.n_waves += self._rung_waves(rows, graph_waves)
             slot = self._counts_host[i % self._counts_host.shape[0]]
             self.lib.dbaz_search_wave_counts(self._h, C.c_void_p(slot.data_ptr()), self._stream())
             ev = torch.cuda.Event()
@@ -459,20 +459,26 @@ class Engine:
                 want = min(busy, int(int(slot0[2]) * self.ROW_MARGIN) + 32)
                 rows = self._pick_rows(ladder, want, id(evaluator))
 
-    def _ladder_graphs(self, evaluator, graph_waves, noise, coeff):
+    def _ladder_graphs(self, evaluator, graph_waves, noise, coeff, short_tail=True):
         """{batch rows: CUDA graph of `graph_waves` [step -> evaluator] waves} for every rung of the ladder (compact mode).
         Every batch size is captured up front: capturing re-binds the search head and idles all trees."""
-        key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, 1, self._mode_key(), "ladder", self.LADDER_STEPS)
+        key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, 1, self._mode_key(), "ladder", self.LADDER_STEPS,
+               short_tail)
         if key not in self._graphs:
             graphs = {}
             for rows in self._ladder():
                 self._batch_rows = rows
                 try:
-                    graphs[rows] = self._capture(evaluator, graph_waves, noise, coeff, 1)
+                    graphs[rows] = self._capture(evaluator, self._rung_waves(rows, graph_waves) if short_tail else graph_waves, noise, coeff, 1)
                 finally:
                     self._batch_rows = None
             self._graphs[key] = (graphs, evaluator)
         return self._graphs[key][0]
+
+    def _rung_waves(self, rows, graph_waves):
+        """Waves per graph replay of a rung: the small rungs run at the end of a search, where the host's decision lag
+        (two replays) is pure overhead once the last tree has finished, so their graphs are shorter."""
+        return max(1, graph_waves // 4) if rows * 8 <= self.n_games else graph_waves
 
     def _pick_rows(self, ladder, want, ev_id):
         """The batch size for waves that are expected to ask for `want` rows: among the rungs that hold at least

@@ -334,7 +334,7 @@ class BatchedSelfPlay:
             eng._noise_buf = torch.zeros((n, A), dtype=torch.float64, device=dev)
         noise_buf = eng._noise_buf
         noise_arg = noise_buf if alpha > 0 else None  # alpha <= 0: the reference mixes the scalar 0.0 in (float32 arithmetic)
-        graphs = eng._ladder_graphs(self.ev, self.graph_waves, noise_arg, coeff)
+        graphs = eng._ladder_graphs(self.ev, self.graph_waves, noise_arg, coeff, short_tail=False)  # a small batch is no tail here
         ladder = eng._ladder()
         per_wave = 1 + int(getattr(self.ev, "engine_launches", 0))
 
