@@ -366,6 +366,7 @@ def main():
                      + ((1 - f_term) * 16 * A + f_miss * 16 * A if use_cache else 0))
     roof = None
     ablation = None
+    net_roof = None
     if rank == 0:
         eng.reset_roots(roots)
         eng.clear_eval_cache()
@@ -406,6 +407,30 @@ def main():
                 "kernel_us": k_ms * 1e3, "algorithmic_bytes_per_sim": bytes_per_sim, "mean_path_nodes": P,
                 "terminal_leaf_frac": f_term, "cache_hit_frac": f_hit, "share_of_step": k_ms * waves_per_step / (ms / args.steps),
                 "sims_per_launch": sims_per_launch, "launches_per_step": waves_per_step}
+        # ---- the evaluator (library tensor-core kernels between the engine's stem and heads kernels) at full width:
+        # FLOPs per position from BASELINE.md (torch FlopCounterMode), timed here as a graph of 8 calls
+        net_roof = None
+        flops_pos = {("simple", "3x3"): 62.9e6, ("resnet", "3x3"): 47.3e6, ("resnet", "5x5"): 106.5e6}.get((args.net, args.board))
+        if flops_pos and args.net != "fake":
+            eng._batch_rows = None
+            for _ in range(3):
+                ev(eng)
+            torch.cuda.synchronize()
+            gnet = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gnet):
+                for _ in range(8):
+                    ev(eng)
+            gnet.replay()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); gnet.replay(); gnet.replay(); b.record()
+            torch.cuda.synchronize()
+            net_us = a.elapsed_time(b) / 16 * 1e3
+            del gnet
+            tf = args.games * flops_pos / net_us / 1e6
+            tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            net_roof = {"bound": "tensor", "kernel": "evaluator, %d leaves: library conv/GEMM kernels + k_nn_stem_mma + k_nn_heads" % args.games,
+                        "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "us_per_batch": net_us,
+                        "peak_source": "measured, sustained bf16" if peaks else "fallback", "flops_per_position": flops_pos}
         if use_cache and not args.no_ablation and world == 1:
             # the same step (a) with the table switched off (fixed wave loop, row == tree): what the cache buys, and
             # (b) with the table on but every evaluator batch at full width, i.e. at the batch size of (a): the cache and
@@ -502,7 +527,7 @@ def main():
                         "h2d_bytes_per_step": int(roots_host.numel() * 8 + noise_pool[0].numel() * 8),
                         "d2h_bytes_per_step": int(visits_host.numel() * 4),
                         "api": "Engine.reset_roots(host roots) + Engine.run_search(host Dirichlet noise) + root_visits -> host"},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ablation": ablation}
+                "gpu_launches": launches, "roofline": roof, "roofline_net": net_roof, "cpu_baseline": cpu, "clocks": clocks, "ablation": ablation}
         if c_rate is not None:
             line["cpu_c_oracle_1core_sims_per_sec"] = c_rate
         emit(line)
