@@ -1009,7 +1009,7 @@ __global__ void k_reset_roots(Board b, TreeArgs ta, const dbaz_state* __restrict
 // memory); (2) prefix sum of the mark bits gives new indices; (3) nodes move front-to-back in
 // chunks of one node per warp (all loads of a chunk complete before its stores; new <= old so
 // nothing unread is overwritten), remapping parent and child indices on the fly.
-constexpr int ADV_THREADS = 256;
+constexpr int ADV_THREADS = 1024;
 template <int NW>
 __global__ void __launch_bounds__(ADV_THREADS)
 k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reuse) {

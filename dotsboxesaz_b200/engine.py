@@ -380,6 +380,7 @@ class Engine:
             if key not in self._graphs:
                 # the evaluator is stored next to its graph: a live reference keeps id() from being recycled
                 self._graphs[key] = (self._capture(evaluator, graph_waves, noise, coeff, pending), evaluator)
+                self._trim_graphs()
             self.begin(num_reads, noise, coeff, pending)
             g = self._graphs[key][0]
             per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
@@ -473,6 +474,7 @@ class Engine:
                 finally:
                     self._batch_rows = None
             self._graphs[key] = (graphs, evaluator)
+            self._trim_graphs()
         return self._graphs[key][0]
 
     def _rung_waves(self, rows, graph_waves):
@@ -496,6 +498,14 @@ class Engine:
             if score > best_score * 1.0001 or (abs(score - best_score) <= best_score * 1e-4 and r > best):
                 best, best_score = r, score
         return best
+
+    MAX_GRAPH_SETS = 6
+
+    def _trim_graphs(self):
+        """Captured graphs (and the evaluators they keep alive) of configurations not used for a while are dropped,
+        oldest first: a coach loop builds a new evaluator every generation."""
+        while len(self._graphs) > self.MAX_GRAPH_SETS:
+            self._graphs.pop(next(iter(self._graphs)))
 
     def _mode_key(self):
         return (self.compact, self.max_inline, self.eval_cache_log2)
