@@ -459,15 +459,18 @@ def main():
     # resident loop, eval cache emptied before the timed batch; the clock stops when the (planes, pi, z) samples are in
     # host memory.
     selfplay = None
-    node_bytes = eng.node_bytes
+    node_bytes, eng_A = eng.node_bytes, eng.A
     if not args.no_selfplay and args.net != "fake":
         from dotsboxesaz_b200 import self_play as sp_mod
         node_bytes = eng.node_bytes
         eng.close()
         del eng
         torch.cuda.empty_cache()
-        sp_games = args.selfplay_games
-        eng_sp = engine.Engine((L, C), n_games=sp_games, max_nodes=args.selfplay_nodes, device=dev, eval_cache=use_cache)
+        # concurrent games: as asked, but the node pools must fit beside the eval cache (80 GB budget)
+        sp_nodes = args.selfplay_nodes if eng_A <= 32 else max(args.selfplay_nodes, 6144)
+        fit = int(80e9 // (sp_nodes * node_bytes))
+        sp_games = max(256, min(args.selfplay_games, fit // 1024 * 1024 if fit >= 1024 else fit))
+        eng_sp = engine.Engine((L, C), n_games=sp_games, max_nodes=sp_nodes, device=dev, eval_cache=use_cache)
         eng_sp.set_mode(False, args.max_inline)
         eng_sp.LADDER_STEPS = args.ladder_steps
         ev_sp = (FusedSimpleNN if args.net == "simple" else FusedResNetZero)(model, eng_sp, dtype=dt) if args.net_plan == "fused" \
