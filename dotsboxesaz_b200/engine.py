@@ -399,7 +399,8 @@ class Engine:
     # then halvings down to 64 rows
     LADDER_STEPS = 16
     ROW_MARGIN = 1.125
-    UNDERSIZE = 0.9          # a batch may be this much smaller than the rows expected, if that serves more rows per microsecond
+    UNDERSIZE = 0.9          # a batch may be this much smaller than the rows expected ...
+    UNDERSIZE_GAIN = 1.05    # ... if it serves this much more rows per microsecond than the best batch that holds them
     WAVE_OVERHEAD_US = 40.0  # per-wave cost that does not depend on the batch (step kernel), for the same trade-off
 
     def _ladder(self):
@@ -483,20 +484,24 @@ class Engine:
         return max(1, graph_waves // 4) if rows * 8 <= self.n_games else graph_waves
 
     def _pick_rows(self, ladder, want, ev_id):
-        """The batch size for waves that are expected to ask for `want` rows: among the rungs that hold at least
-        UNDERSIZE * want rows, the one that serves the most rows per microsecond of evaluator time (library GEMM/conv
-        kernels are step functions of the batch: a rung just past a tile-wave boundary costs a whole extra wave).  A rung
-        below `want` is allowed because the surplus leaves simply wait a wave (dbaz_search_set_batch_rows)."""
-        best, best_score = None, -1.0
-        for r in ladder:
-            if r < self.UNDERSIZE * want and r != ladder[0]:
-                continue
+        """The batch size for waves that are expected to ask for `want` rows: the rung that holds them and serves the most
+        rows per microsecond of evaluator time -- or a rung up to 10 % short of `want` when that is clearly cheaper per row
+        served (library GEMM/conv kernels are step functions of the batch: a rung just past a tile-wave boundary costs a
+        whole extra wave).  A short rung is allowed because the surplus leaves simply wait a wave
+        (dbaz_search_set_batch_rows); it has to win by UNDERSIZE_GAIN because those leaves' trees fall a wave behind."""
+        def score(r):
             us = self._eval_us.get((ev_id, r))
-            if us is None:
-                return min(x for x in ladder if x >= want)
-            score = min(r, want) / (us + self.WAVE_OVERHEAD_US)
-            if score > best_score * 1.0001 or (abs(score - best_score) <= best_score * 1e-4 and r > best):
-                best, best_score = r, score
+            return None if us is None else min(r, want) / (us + self.WAVE_OVERHEAD_US)
+        fit = [r for r in ladder if r >= want] or [ladder[0]]
+        scored = [(score(r), r) for r in fit]
+        if any(sc is None for sc, _ in scored):
+            return min(fit)
+        best_sc, best = max(scored)
+        for r in ladder:
+            if self.UNDERSIZE * want <= r < want:
+                sc = score(r)
+                if sc is not None and sc > best_sc * self.UNDERSIZE_GAIN:
+                    best_sc, best = sc / self.UNDERSIZE_GAIN * 1.0001, r  # a further short rung must beat this one outright
         return best
 
     MAX_GRAPH_SETS = 6

@@ -121,6 +121,9 @@ def main():
     torch.cuda.synchronize()
     net_us = a.elapsed_time(b) / 10 * 1e3
     flops = 106.5e6  # per position, BASELINE.md
+    sched = getattr(eng, "last_schedule", [])
+    print("schedule (rows/busy per replay):", " ".join("%d/%d" % rb for rb in sched[::4]), file=sys.stderr)
+    print("evaluator us per rung:", {r: round(u) for (_, r), u in sorted(eng._eval_us.items(), key=lambda kv: -kv[0][1])}, file=sys.stderr)
     print(json.dumps({"config": "configs[3]: 5x5 boxes, %d concurrent games, %d sims/move, ResNetZero(64ch x 20 blocks) bf16, one UCT_search from "
                                 "synthetic roots, Dirichlet(0.8, 0.25), eval cache 2^%d emptied per step" % (args.games, args.sims, args.eval_cache),
                       "ms_per_search": ms, "sims_per_sec": sims / ms * 1e3, "waves": (eng.n_waves - w0) / reps,
