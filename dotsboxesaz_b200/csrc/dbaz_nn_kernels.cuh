@@ -6,6 +6,8 @@
 // Reference semantics: dots_boxes/dots_boxes_nn.py:85-98 (x = bn(relu(conv(x)))), nn.py:49-58,
 // nn.py:155-160 (p = exp(log_softmax), v = tanh).
 #pragma once
+#include <cuda/barrier>
+
 #include "dbaz_device.cuh"
 
 namespace dbaz {
@@ -384,13 +386,22 @@ k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /
     unsigned char* stage_all = code_s + ((HW * STEM_K + 15) & ~15);                    // [STEM_WARPS][16][STAGE_ROW]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 
-    // ---- B fragments, already in fragment order (k_nn_stem_mma_pack): a straight 16-byte copy
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(w48);
-        uint4* dst = reinterpret_cast<uint4*>(b_s);
-        const int n16 = (cout / 8) * 3 * 32 / 2;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    // ---- B fragments, already in fragment order (k_nn_stem_mma_pack): ONE bulk asynchronous copy (TMA, cp.async.bulk)
+    // global -> shared, issued by thread 0 and completed on an mbarrier while the other threads build the code table
+    using block_barrier = cuda::barrier<cuda::thread_scope_block>;
+    __shared__ block_barrier b_ready;
+    if (threadIdx.x == 0) {
+        init(&b_ready, blockDim.x);
+        cuda::device::experimental::fence_proxy_async_shared_cta();
+    }
+    __syncthreads();
+    block_barrier::arrival_token b_token;
+    if (threadIdx.x == 0) {
+        const unsigned b_bytes = (unsigned)((cout / 8) * 3 * 32 * sizeof(uint2));  // a multiple of 16; both ends 16-byte aligned
+        cuda::device::memcpy_async_tx(reinterpret_cast<uint4*>(b_s), reinterpret_cast<const uint4*>(w48), cuda::aligned_size_t<16>(b_bytes), b_ready);
+        b_token = cuda::device::barrier_arrive_tx(b_ready, 1, b_bytes);
+    } else {
+        b_token = b_ready.arrive();
     }
     // ---- code table
     for (int i = threadIdx.x; i < HW * STEM_K; i += blockDim.x) {
@@ -403,6 +414,7 @@ k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /
         } else if (k == 36) c = 129;
         code_s[i] = c;
     }
+    b_ready.wait(std::move(b_token));  // weights landed (and every thread has arrived)
     __syncthreads();
 
     unsigned char* stage = stage_all + (size_t)warp * 16 * STAGE_ROW;
