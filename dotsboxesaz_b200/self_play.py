@@ -443,6 +443,8 @@ class BatchedSelfPlay:
         return torch.cat(planes), torch.cat(pis), torch.cat(zs), torch.cat(slots), torch.cat(mis)
 
     def get_games_moves(self):
+        if not self.played_games and getattr(self, "_device_hist", None) is not None:
+            self._rows_from_device(False)
         moves, vcs = [], []
         for _, mv, vis, _ in self.played_games:
             moves.extend(mv)
@@ -451,8 +453,54 @@ class BatchedSelfPlay:
 
     def get_datasets(self, generation, with_features=True):
         if not self.rows and getattr(self, "_device_hist", None) is not None:
-            self._rows_from_device(with_features)
+            return self._dataset_from_device(generation, with_features)
         return _dataset(self.rows, generation, with_features)
+
+    def _dataset_from_device(self, generation, with_features=True):
+        """The DataFrame of self_play.py:95-156 straight from the device-resident history of play_games_device() /
+        play_games_async(): the same columns, dtypes, MultiIndex and row order (game by game, move by move) as
+        _dataset(_rows_from_device()), built from whole arrays instead of one Python dict per row."""
+        h, eng = self._device_hist, self.eng
+        n, A = eng.n_games, eng.A
+        act = torch.stack(h["active"]).t().contiguous()                       # [n, M]
+        sel = act.reshape(-1)
+        M = act.shape[1]
+        states = torch.stack(h["states"])                                     # [M, n, 4]
+        to_play_mn = states.view(torch.uint8).reshape(M, n, 32)[:, :, 20]
+        pick = lambda t: t.transpose(0, 1).reshape((n * M,) + tuple(t.shape[2:]))[sel].cpu().numpy()
+        vis = pick(torch.stack(h["visits"]))
+        stats = pick(torch.stack(h["stats"]))
+        q = pick(torch.stack(h["q"]))
+        player = pick(to_play_mn).astype(np.int8)
+        mv = torch.stack(h["moves"])                                          # [M, n]: the move played FROM position m
+        prev = torch.cat([torch.full_like(mv[:1], -1), mv[:-1]], 0)           # ... the one that LED to position m
+        move = pick(prev).astype(np.int16)
+        g_of = torch.arange(n, device=act.device).unsqueeze(1).expand(n, M).reshape(-1)[sel].cpu().numpy()
+        m_of = torch.arange(M, device=act.device).unsqueeze(0).expand(n, M).reshape(-1)[sel].cpu().numpy()
+        res = h["result"].cpu().numpy().astype(np.int64)
+        winner = eng.states_to_numpy(h["final"])["just_played"]
+        z = np.where(player == winner[g_of], res[g_of], -res[g_of])
+        games = np.asarray(h["games_idxs"])
+        if isinstance(generation, (list, tuple)):
+            gen = np.where(player == 0, generation[0], generation[1]).astype(np.int16)
+        else:
+            gen = np.full(len(g_of), generation, dtype=np.int16)
+        cols = {"generation": gen, "game_idx": games[g_of].astype(np.int16), "move_idx": m_of.astype(np.int16), "move": move, "player": player}
+        if with_features:
+            feats = torch.stack([eng.features(s, torch.int16) for s in h["states"]]).reshape(M, n, -1)
+            feats = pick(feats)
+            cols.update({"x_" + str(i): feats[:, i] for i in range(feats.shape[1])})
+        vs = vis.sum(1, keepdims=True).astype(np.float64)
+        pi = vis / np.where(vs == 0, 1.0, vs)
+        cols.update({"pi_" + str(i): pi[:, i] for i in range(A)})
+        cols["z"] = z
+        cols["max_deepness"] = stats[:, 1].astype(np.int16)
+        cols["tree_size"] = stats[:, 2].astype(np.int32)
+        cols["terminal_count"] = stats[:, 3].astype(np.int32)
+        cols["q_value"] = q.astype(np.float32)
+        df = pd.DataFrame(cols)
+        df.set_index(["generation", "game_idx", "move_idx"], inplace=True)
+        return df
 
     def _rows_from_device(self, with_features=True):
         """Turn the device-resident history of play_games_device() into the row dicts of get_datasets()."""

@@ -247,6 +247,15 @@ def test_device_resident_selfplay_is_valid_play(api, mode):
             carried = max(int(visits[m, g][moves[m, g]]) - 1, 0) if visits[m, g][moves[m, g]] > 0 else 0
             og.play_(int(moves[m, g]))
         assert og.result() == int(res[g])
+    # the vectorised DataFrame builder against the row-by-row one (same columns, dtypes, index and order)
+    import pandas as pd
+    for gen in (3, [2, 5]):
+        fast = bsp.get_datasets(gen, True)
+        if not bsp.rows:
+            bsp._rows_from_device(True)
+        slow = api["self_play"]._dataset(bsp.rows, gen, True)
+        bsp.rows = []
+        pd.testing.assert_frame_equal(fast, slow, check_exact=True)
     eng.close()
 
 
