@@ -106,7 +106,7 @@ struct TreeArgs {
     uint32_t cache_mask;
     int cache_vcell;
     // lock-step bookkeeping, self-resetting (the last CTA of a launch publishes and zeroes it):
-    // ctr[0] rows asked for, ctr[1] trees still busy, ctr[2] CTAs done | ctr[4] rows asked for by the last launch,
+    // ctr[0] rows asked for, ctr[1] trees still busy, ctr[2] warps done | ctr[4] rows asked for by the last launch,
     // ctr[5] busy trees after it, ctr[6] largest ctr[4] since the host last read it, ctr[7] largest node pool use seen by a re-root
     int* ctr;
     int compact;          // 1: a tree's pending leaf goes to row atomicAdd(ctr[0]) instead of row == tree (pending == 1 only)
@@ -710,7 +710,7 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
 }
 
 // ---------------------------------------------------------------- kernels
-constexpr int TREE_WARPS = 4;  // trees per CTA
+constexpr int TREE_WARPS = 1;  // trees per CTA: one, so that a tree with a long chain holds up nobody's CTA slot
 
 template <int APL, int NW>
 __global__ void __launch_bounds__(TREE_WARPS * 32)
@@ -938,13 +938,12 @@ __device__ __forceinline__ bool search_step_waves(const Board& b, const TreeArgs
 }
 
 template <int APL, int NW>
-__global__ void __launch_bounds__(TREE_WARPS * 32, APL == 1 ? 7 : (APL == 2 ? 5 : 3))
+__global__ void __launch_bounds__(TREE_WARPS * 32, (APL == 1 ? 28 : (APL == 2 ? 20 : 12)) / TREE_WARPS)
 k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this search, <= ta.max_pending */,
               const float* __restrict__ priors, const float* __restrict__ values,
               const double* __restrict__ noise, double coeff, void* __restrict__ planes, int dtype, int layout,
               dbaz_state* __restrict__ leaf_states, int8_t* __restrict__ leaf_kind) {
     __shared__ double sh_all[TREE_WARPS][DBAZ_MAX_ACTIONS];
-    __shared__ int s_busy[TREE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * TREE_WARPS + warp;
     bool busy = false;
@@ -956,16 +955,12 @@ k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this sea
             busy = search_step_waves<APL, NW>(b, ta, t, pending, priors, values, noise, coeff, planes, dtype, layout, leaf_states,
                                               leaf_kind, sh_all[warp], lane);
     }
-    // ---- wave bookkeeping: the last CTA to finish publishes {rows handed out, busy trees} and re-arms the counters
-    if (lane == 0) s_busy[warp] = busy ? 1 : 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int nb = 0;
-#pragma unroll
-        for (int w = 0; w < TREE_WARPS; ++w) nb += s_busy[w];
-        if (nb) atomicAdd(&ta.ctr[1], nb);
+    // ---- wave bookkeeping, per warp (no CTA barrier: a warp leaves as soon as its tree is done, so a long chain keeps
+    // one warp slot busy, not four): the last warp of the launch publishes {rows asked for, busy trees} and re-arms
+    if (lane == 0) {
+        if (busy) atomicAdd(&ta.ctr[1], 1);
         __threadfence();
-        if (atomicAdd(&ta.ctr[2], 1) == (int)gridDim.x - 1) {
+        if (atomicAdd(&ta.ctr[2], 1) == (int)(gridDim.x * TREE_WARPS) - 1) {
             __threadfence();
             const int rows = atomicExch(&ta.ctr[0], 0);
             ta.ctr[4] = rows;
