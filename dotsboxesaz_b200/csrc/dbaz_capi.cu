@@ -149,7 +149,7 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     const int A = 2 * (L + 1) * (C + 1);
     if (A > DBAZ_MAX_ACTIONS) return fail(nullptr, "board too large: 2*(L+1)*(C+1) must be <= 128");
     if (L * C > 16000) return fail(nullptr, "board too large");
-    if (cfg->n_games < 1) return fail(nullptr, "n_games must be >= 1");
+    if (cfg->n_games < 1 || cfg->n_games >= (1 << 20)) return fail(nullptr, "n_games must be in [1, 2^20) (trees per engine; game-rule calls take any n)");
     if (cfg->max_nodes < 2 || cfg->max_nodes > 65536) return fail(nullptr, "max_nodes must be in [2, 65536]");
     const int max_pending = cfg->max_pending > 0 ? cfg->max_pending : 1;
     if (max_pending > DBAZ_MAX_PENDING) return fail(nullptr, "max_pending too large");

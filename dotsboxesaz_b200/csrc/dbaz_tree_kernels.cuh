@@ -106,7 +106,7 @@ struct TreeArgs {
     uint32_t cache_mask;
     int cache_vcell;
     // lock-step bookkeeping, self-resetting (the last CTA of a launch publishes and zeroes it):
-    // ctr[0] rows asked for, ctr[1] trees still busy, ctr[2] warps done | ctr[4] rows asked for by the last launch,
+    // ctr[0..1] one 64-bit word {bits 40+: rows asked for, 20-39: trees still busy, 0-19: warps done} | ctr[4] rows asked for by the last launch,
     // ctr[5] busy trees after it, ctr[6] largest ctr[4] since the host last read it, ctr[7] largest node pool use seen by a re-root
     int* ctr;
     int compact;          // 1: a tree's pending leaf goes to row atomicAdd(ctr[0]) instead of row == tree (pending == 1 only)
@@ -824,7 +824,7 @@ __device__ __forceinline__ bool search_step_seq(const Board& b, const TreeArgs& 
                 int64_t row = t;
                 if (compact) {
                     int r = 0;
-                    if (lane == 0) r = atomicAdd(&ta.ctr[0], 1);
+                    if (lane == 0) r = (int)(atomicAdd(reinterpret_cast<unsigned long long*>(ta.ctr), 1ull << 40) >> 40);
                     r = __shfl_sync(0xffffffffu, r, 0);
                     if (r >= ta.batch_rows) {
                         // the evaluator's batch is full: this selection is dropped and repeated in the next wave.
@@ -956,17 +956,18 @@ k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this sea
                                               leaf_kind, sh_all[warp], lane);
     }
     // ---- wave bookkeeping, per warp (no CTA barrier: a warp leaves as soon as its tree is done, so a long chain keeps
-    // one warp slot busy, not four): the last warp of the launch publishes {rows asked for, busy trees} and re-arms
+    // one warp slot busy, not four).  Rows asked for, busy trees and finished warps share ONE 64-bit word, so a single
+    // atomic per warp keeps them consistent without a fence; the warp that completes the count publishes and re-arms.
     if (lane == 0) {
-        if (busy) atomicAdd(&ta.ctr[1], 1);
-        __threadfence();
-        if (atomicAdd(&ta.ctr[2], 1) == (int)(gridDim.x * TREE_WARPS) - 1) {
-            __threadfence();
-            const int rows = atomicExch(&ta.ctr[0], 0);
+        unsigned long long* word = reinterpret_cast<unsigned long long*>(ta.ctr);
+        const unsigned long long inc = 1ull | (busy ? (1ull << 20) : 0ull);
+        const unsigned long long now = atomicAdd(word, inc) + inc;
+        if ((now & 0xfffffull) == (unsigned long long)(gridDim.x * TREE_WARPS)) {
+            const int rows = (int)(now >> 40);
             ta.ctr[4] = rows;
-            ta.ctr[5] = atomicExch(&ta.ctr[1], 0);
+            ta.ctr[5] = (int)((now >> 20) & 0xfffffull);
             if (rows > ta.ctr[6]) ta.ctr[6] = rows;
-            ta.ctr[2] = 0;
+            *word = 0ull;  // nobody else touches it before the next launch
         }
     }
 }
