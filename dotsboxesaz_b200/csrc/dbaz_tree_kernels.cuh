@@ -853,17 +853,15 @@ __device__ __forceinline__ bool search_step_seq(const Board& b, const TreeArgs& 
     if (lane == 0) {
         if (leaf_kind && !compact) leaf_kind[t] = (int8_t)T.n_pending;
         store_hot(ta.trees + t, T);
-        if (ws.sims) {  // tree statistics of the simulations this launch finished (only ever touched here)
+        if (ws.sims) {
+            // tree statistics of the simulations this launch finished: reductions without a return value (RED), so the
+            // warp does not wait for the old values of fields only this warp ever touches
             TreeRec* G = ta.trees + t;
-            uint4 st = reinterpret_cast<uint4*>(G)[2];  // {deepness_correction, terminal_count, tree_size, total_term}
-            st.y += (uint32_t)ws.term; st.w += (uint32_t)ws.term;
-            reinterpret_cast<uint4*>(G)[2] = st;
-            if (ws.maxdeep > G->max_deepness) G->max_deepness = ws.maxdeep;
-            uint4 tot = reinterpret_cast<uint4*>(G)[3];  // {total_sims, cache_hits, total_path lo, hi}
-            tot.x += (uint32_t)ws.sims; tot.y += (uint32_t)ws.hits;
-            const unsigned long long tp = (((unsigned long long)tot.w << 32) | tot.z) + (unsigned long long)ws.path;
-            tot.z = (uint32_t)tp; tot.w = (uint32_t)(tp >> 32);
-            reinterpret_cast<uint4*>(G)[3] = tot;
+            if (ws.term) { atomicAdd(&G->terminal_count, ws.term); atomicAdd(&G->total_term, ws.term); }
+            atomicMax(&G->max_deepness, ws.maxdeep);
+            atomicAdd(&G->total_sims, (uint32_t)ws.sims);
+            if (ws.hits) atomicAdd(&G->cache_hits, (uint32_t)ws.hits);
+            atomicAdd(&G->total_path, (unsigned long long)ws.path);
         }
     }
     return T.n_pending > 0 || T.sims_left > 0;
