@@ -129,3 +129,29 @@ def test_adaptive_ladder_and_default_cache_size():
     assert self_play.default_eval_cache(p) == 0
     p2 = DotDict({"self_play": {"mcts": {}}, "game": {"clazz": G77}})
     assert self_play.default_eval_cache(p2) == 0                   # A = 128 > 88: no table
+
+
+def test_pick_rows_prefers_cheap_rungs_and_holds_the_rows():
+    """Engine._pick_rows (host logic of the adaptive loop): with a measured evaluator-time curve that has tile-wave steps,
+    the chosen rung holds the expected rows unless a rung at most 10 % short is at least 5 % cheaper per row served."""
+    from dotsboxesaz_b200 import engine
+    e = object.__new__(engine.Engine)
+    e.n_games, e.LADDER_STEPS = 4096, 16
+    lad = e._ladder()
+    curve = {4096: 223.0, 3840: 209.2, 3584: 212.8, 3328: 181.1, 3072: 180.6, 2816: 179.3, 2560: 177.2, 2304: 146.4, 2048: 141.2,
+             1792: 138.8, 1536: 130.1, 1280: 130.0, 1024: 103.8, 768: 80.6, 512: 70.9, 256: 56.4, 128: 52.5, 64: 51.1}
+    e._eval_us = {(1, r): curve[r] for r in lad}
+    assert e._pick_rows(lad, 4096, 1) == 4096
+    assert e._pick_rows(lad, 2400, 1) == 2304      # 2560 would cost a second wave of tiles for 96 more rows
+    assert e._pick_rows(lad, 2000, 1) == 2048
+    assert e._pick_rows(lad, 10, 1) == 64
+    for want in range(1, 4097, 37):
+        r = e._pick_rows(lad, want, 1)
+        assert r in lad and r >= engine.Engine.UNDERSIZE * want
+    # a linear curve never undersizes where the ladder is dense (rungs 256 apart)
+    e._eval_us = {(1, r): 50.0 + 0.15 * r for r in lad}
+    for want in range(1100, 4097, 53):
+        assert e._pick_rows(lad, want, 1) >= want
+    # without measurements: the smallest rung that holds the rows
+    e._eval_us = {}
+    assert e._pick_rows(lad, 2400, 1) == 2560
