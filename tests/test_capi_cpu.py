@@ -148,10 +148,15 @@ def test_pick_rows_prefers_cheap_rungs_and_holds_the_rows():
     for want in range(1, 4097, 37):
         r = e._pick_rows(lad, want, 1)
         assert r in lad and r >= engine.Engine.UNDERSIZE * want
-    # a linear curve never undersizes where the ladder is dense (rungs 256 apart)
-    e._eval_us = {(1, r): 50.0 + 0.15 * r for r in lad}
-    for want in range(1100, 4097, 53):
-        assert e._pick_rows(lad, want, 1) >= want
+    # whatever the curve, the choice serves at least as many rows per microsecond as the smallest rung that holds them all
+    for us in (curve, {r: 50.0 + 0.15 * r for r in lad}):
+        e._eval_us = {(1, r): us[r] for r in lad}
+        score = lambda r, want: min(r, want) / (us[r] + engine.Engine.WAVE_OVERHEAD_US)
+        for want in range(1, 4097, 53):
+            r = e._pick_rows(lad, want, 1)
+            assert score(r, want) >= score(min(x for x in lad if x >= want), want) - 1e-12
+            if r < want:
+                assert score(r, want) > engine.Engine.UNDERSIZE_GAIN * max(score(x, want) for x in lad if x >= want)
     # without measurements: the smallest rung that holds the rows
     e._eval_us = {}
     assert e._pick_rows(lad, 2400, 1) == 2560
