@@ -8,7 +8,16 @@ A "step" is one UCT_search (`--sims` simulations per tree, default 800) for ever
 `--games` concurrent games of a GPU (default 4096, 3x3 boxes = BASELINE configs[1]) from synthetic
 root positions, with Dirichlet root noise (0.8, 0.25) and the reference's SimpleNN (random-init,
 seed 0) as leaf evaluator.  One process per GPU; games are sharded by index, there is no data-path
-collective (weak scaling).  Rank 0 prints ONE JSON line.
+collective (weak scaling).  Rank 0 prints ONE JSON line (stdout carries nothing else).
+
+The engine's eval cache (the reference's LRU of net outputs, utils/proxies.py:23-26) is part of the path and is
+EMPTIED at the start of every step, inside the timed region.  Keys of the line beyond the contract:
+  roofline       k_search_step against the HBM roofline (algorithmic bytes per simulation x simulations per launch /
+                 mean launch duration, CUDA events around every launch with the real evaluator in between)
+  roofline_net   the evaluator at full width against the sustained bf16 tensor peak
+  cpu_baseline   oracle/py_port.py on the host cores, bounded sample (N=1 only)
+  ablation       the same step with the eval cache switched off, and whether the visit counts agree
+  selfplay       whole self-play games per hour (`--selfplay-games` concurrent games per GPU, samples to the host)
 """
 import argparse
 import json
