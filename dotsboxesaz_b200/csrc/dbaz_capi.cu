@@ -450,8 +450,12 @@ int dbaz_search_step(dbaz_engine* e, const float* priors, const float* values, v
     if (dtype < DBAZ_F32 || dtype > DBAZ_I16 || layout < 0 || layout > 1) return fail(e, "bad dtype/layout");
     DeviceGuard guard(e->cfg.device);
     const int grid = blocks_for(e->ta.n_trees, TREE_WARPS);
-    DBAZ_DISPATCH(e, (k_search_step<APL, NW><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(
-                         e->board, e->ta, e->pending, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, leaf_kind)));
+    if (e->pending == 1)
+        DBAZ_DISPATCH(e, (k_search_step<APL, NW, true><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(
+                             e->board, e->ta, 1, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, leaf_kind)));
+    else
+        DBAZ_DISPATCH(e, (k_search_step<APL, NW, false><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(
+                             e->board, e->ta, e->pending, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, leaf_kind)));
     return launch_ok(e, "k_search_step");
 }
 

@@ -935,7 +935,9 @@ __device__ __forceinline__ bool search_step_waves(const Board& b, const TreeArgs
     return T.n_pending > 0 || T.sims_left > 0;
 }
 
-template <int APL, int NW>
+// SEQ: max_pending_evals == 1 (search_step_seq); else the K-wave path.  Two kernels rather than one branch: each gets its
+// own register allocation and half the code.
+template <int APL, int NW, bool SEQ>
 __global__ void __launch_bounds__(TREE_WARPS * 32, (APL == 1 ? 28 : (APL == 2 ? 20 : 12)) / TREE_WARPS)
 k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this search, <= ta.max_pending */,
               const float* __restrict__ priors, const float* __restrict__ values,
@@ -946,7 +948,7 @@ k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this sea
     const int t = blockIdx.x * TREE_WARPS + warp;
     bool busy = false;
     if (t < ta.n_trees) {
-        if (pending == 1)
+        if (SEQ)
             busy = search_step_seq<APL, NW>(b, ta, t, priors, values, noise, coeff, planes, dtype, layout, leaf_states, leaf_kind,
                                             sh_all[warp], lane);
         else
