@@ -417,8 +417,8 @@ class Engine:
     def _run_adaptive(self, num_reads, evaluator, noise, coeff, graph_waves):
         """The wave loop with a shrinking evaluator batch.  Leaves are handed over in compact rows (set_mode), the step
         kernel publishes how many trees still have work, and the host -- one graph replay behind the device -- picks
-        the smallest captured batch that holds the rows recent waves asked for (never more than the busy trees; a
-        batch that turns out too small only makes the surplus leaves wait a wave) and stops when no tree is busy.
+        the captured batch for the rows recent waves asked for (_pick_rows; never more than the busy trees; a batch
+        that turns out too small only makes the surplus leaves wait a wave) and stops when no tree is busy.
         The decision for replay i+2 is taken from the counters at the end of replay i, which the host waits for:
         the schedule, and with it every evaluator batch, is reproducible."""
         self.pending = 1
