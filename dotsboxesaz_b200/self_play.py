@@ -665,8 +665,9 @@ def gather_samples(df, dst=0):
 
 
 def default_eval_cache(params):
-    """log2(entries) of the engine's eval cache: `params.self_play.eval_cache_log2` if given (0 = none), else about
-    2 GB worth -- the role of the reference's `nn.max_cache_size` LRU (self_play.py:226-230).  (Only searches with one
+    """log2(entries) of the engine's eval cache: `params.self_play.eval_cache_log2` if given (0 = none), else up to
+    8 GB worth (3x3: 2^24 entries of 512 bytes, the table bench.py runs with; a direct-mapped table wants several slots
+    per insert) -- the role of the reference's `nn.max_cache_size` LRU (self_play.py:226-230).  (Only searches with one
     simulation in flight per tree use the table; generate_games builds its engine that way.)"""
     sp = params.self_play
     want = sp.get("eval_cache_log2", None)
@@ -676,7 +677,7 @@ def default_eval_cache(params):
     A = 2 * (L + 1) * (C + 1)
     if A > 88:
         return 0
-    return max(16, int(np.log2((2 << 30) / (16 * A))))
+    return max(16, int(np.log2((8 << 30) / (16 * A))))
 
 
 def generate_games(hdf_file_name, generation, nn_class, n_games, params, n_workers=None, games_per_workers=10,

@@ -124,7 +124,7 @@ def test_adaptive_ladder_and_default_cache_size():
         BOARD_DIM = (7, 7)
     p = DotDict({"self_play": {"mcts": {"max_async_searches": 64}}, "game": {"clazz": G33}})
     k = self_play.default_eval_cache(p)
-    assert 16 <= k <= 24 and (1 << k) * 16 * 32 <= (2 << 30)      # about 2 GB of 512-byte entries
+    assert k == 24 and (1 << k) * 16 * 32 <= (8 << 30)            # 2^24 entries of 512 bytes = 8 GiB
     p.self_play.eval_cache_log2 = 0
     assert self_play.default_eval_cache(p) == 0
     p2 = DotDict({"self_play": {"mcts": {}}, "game": {"clazz": G77}})
