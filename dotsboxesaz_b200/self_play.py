@@ -423,24 +423,25 @@ class BatchedSelfPlay:
 
     def device_samples(self):
         """(planes int16 [R, 3, L+1, C+1], pi float64 [R, A], z float32 [R], game slot [R], move index [R]) of the last
-        play_games_device() call, still on the device (rows of finished games are dropped)."""
+        play_games_device() / play_games_async() call, still on the device, move by move and slot by slot within a move
+        (positions that were not searched -- finished games -- are dropped).  One features call and one compaction for the
+        whole history."""
         h, eng = self._device_hist, self.eng
-        final_np_tp = None
-        winner = (h["final"].view(torch.uint8).reshape(eng.n_games, 32)[:, 21]).to(torch.int8)  # just_played of the terminal state
-        z_final = h["result"].float()
-        planes, pis, zs, slots, mis = [], [], [], [], []
-        for mi, (st, vis, act) in enumerate(zip(h["states"], h["visits"], h["active"])):
-            idx = torch.nonzero(act).reshape(-1)
-            if idx.numel() == 0:
-                continue
-            to_play = st.view(torch.uint8).reshape(eng.n_games, 32)[:, 20].to(torch.int8)
-            planes.append(eng.features(st, torch.int16)[idx])
-            v = vis[idx].double()
-            pis.append(v / v.sum(1, keepdim=True).clamp_min(1.0))
-            zs.append(torch.where(to_play[idx] == winner[idx], z_final[idx], -z_final[idx]))
-            slots.append(idx)
-            mis.append(torch.full_like(idx, mi))
-        return torch.cat(planes), torch.cat(pis), torch.cat(zs), torch.cat(slots), torch.cat(mis)
+        n = eng.n_games
+        act = torch.stack(h["active"])                                   # [M, n]
+        M = act.shape[0]
+        states = torch.stack(h["states"]).reshape(M * n, 4)
+        idx = torch.nonzero(act.reshape(-1)).reshape(-1)                 # row-major: move index, then slot
+        sel = states[idx].contiguous()
+        planes = eng.features(sel, torch.int16)
+        v = torch.stack(h["visits"]).reshape(M * n, eng.A)[idx].double()
+        pi = v / v.sum(1, keepdim=True).clamp_min(1.0)
+        slot, mi = idx % n, idx // n
+        to_play = sel.view(torch.uint8).reshape(-1, 32)[:, 20].to(torch.int8)
+        winner = (h["final"].view(torch.uint8).reshape(n, 32)[:, 21]).to(torch.int8)[slot]  # just_played of the terminal state
+        z_final = h["result"].float()[slot]
+        z = torch.where(to_play == winner, z_final, -z_final)
+        return planes, pi, z, slot, mi
 
     def get_games_moves(self):
         if not self.played_games and getattr(self, "_device_hist", None) is not None:
