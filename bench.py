@@ -15,7 +15,7 @@ EMPTIED at the start of every step, inside the timed region.  Keys of the line b
   roofline       k_search_step against the HBM roofline (algorithmic bytes per simulation x simulations per launch /
                  mean launch duration, CUDA events around every launch with the real evaluator in between)
   roofline_net   the evaluator at full width against the sustained bf16 tensor peak
-  cpu_baseline   oracle/py_port.py on the host cores, bounded sample (N=1 only)
+  cpu_baseline   the real reference (oracle/_ref, staged by oracle/make_ref.sh; oracle/py_port.py if absent) on the host cores, bounded sample (N=1 only)
   ablation       the same step with the eval cache switched off, and whether the visit counts agree
   selfplay       whole self-play games per hour (`--selfplay-games` concurrent games per GPU, samples to the host)
 """
@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--net-dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--net-plan", default="fused", choices=["fused", "module"],
                     help="fused: library convs/GEMMs + the engine's fused epilogue kernels; module: the plain nn.Module")
+    ap.add_argument("--no-tower", action="store_true", help="ResNetZero: library (cuDNN) convolutions instead of the tcgen05 tower kernel")
     ap.add_argument("--graph-waves", type=int, default=8)
     ap.add_argument("--pending", type=int, default=1,
                     help="max_pending_evals: simulations in flight per tree (1 = strictly sequential, BASELINE configs[1]; "
@@ -85,16 +86,35 @@ def cpu_workers(args):
     return args.cpu_workers if args.cpu_workers > 0 else max(1, min(cores - 1, 64))
 
 
-def run_cpu_sample(args, pool, workers, n_pos, seed0):
-    """Every worker runs `n_pos` searches of the bench workload on the Python restatement of the
-    reference (oracle/py_port.py: asyncio MCTS + age-triggered batching proxy + SimpleNN on CPU,
-    1 torch thread per process -- the reference's own process layout, self_play.py:291-306)."""
+def cpu_impl():
+    """("reference", oracle.ref_driver) when the real reference has been staged in oracle/_ref (oracle/make_ref.sh; it
+    travels to the GPU box with the snapshot), else ("port", oracle.py_port), the Python restatement."""
+    from oracle import ref_driver
+    if ref_driver.available():
+        return "reference", ref_driver
     from oracle import py_port
+    return "port", py_port
+
+
+def cpu_impl_text(kind):
+    if kind == "reference":
+        return ("the UNMODIFIED reference (oracle/_ref = /root/reference staged by oracle/make_ref.sh): mcts.UCT_search + "
+                "utils.proxies.AsyncBatchedProxy(48, 50 ms, 400k LRU) + nn.NeuralNetWrapper + SimpleNN fp32 on CPU, "
+                "max_pending_evals 64, 1 torch thread per process")
+    return ("oracle/py_port.py (Python/NumPy restatement of the reference incl. its 48-batch/50 ms proxy and 400k LRU, SimpleNN "
+            "fp32 on CPU, 1 torch thread per process)")
+
+
+def run_cpu_sample(args, pool, workers, n_pos, seed0):
+    """Every worker runs `n_pos` searches of the bench workload on the reference's own code (or, where oracle/_ref is
+    missing, on its Python restatement): asyncio MCTS + age-triggered batching proxy + SimpleNN on CPU, 1 torch thread
+    per process -- the reference's own process layout, self_play.py:291-306."""
+    _, impl = cpu_impl()
     L, C = (int(x) for x in args.board.split("x"))
     net = "simple" if args.net != "fake" else "fake"
     jobs = [((L, C), args.sims, n_pos, seed0 + w, net, MAX_ROOT_PLIES) for w in range(workers)]
     t0 = time.time()
-    res = pool.map(py_port.worker_search, jobs)
+    res = pool.map(impl.worker_search, jobs)
     wall = time.time() - t0
     sims = sum(r[0] for r in res)
     return sims, wall
@@ -107,11 +127,10 @@ def cpu_baseline(args):
     with ctx.Pool(workers) as pool:
         run_cpu_sample(args, pool, workers, 1, 1000)  # warm-up: imports, torch init
         sims, wall = run_cpu_sample(args, pool, workers, args.cpu_positions, 2000)
-    return {"value": sims / wall, "unit": UNIT, "cores": workers, "kind": "port",
-            "sample": "%d processes x %d UCT_search(%d sims) of the bench workload on oracle/py_port.py "
-                      "(Python/NumPy restatement of the reference incl. its 48-batch/50 ms proxy and 400k LRU, SimpleNN fp32 "
-                      "on CPU, 1 torch thread per process); %d sims in %.1f s wall"
-                      % (workers, args.cpu_positions, args.sims, sims, wall),
+    kind = cpu_impl()[0]
+    return {"value": sims / wall, "unit": UNIT, "cores": workers, "kind": kind,
+            "sample": "%d processes x %d UCT_search(%d sims) of the bench workload on %s; %d sims in %.1f s wall"
+                      % (workers, args.cpu_positions, args.sims, cpu_impl_text(kind), sims, wall),
             "host_cores": os.cpu_count()}
 
 
@@ -147,10 +166,8 @@ def reference_arm(args):
             "impl": "reference",
             "config": {"workload": workload_name(args), "board": args.board, "sims_per_move": args.sims,
                        "step": "each of %d processes runs %d UCT_search(%d) on a synthetic root" % (workers, per_step, args.sims)},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
-                             "sample": "oracle/py_port.py (Python/NumPy restatement of the reference; the reference itself is "
-                                       "Python and /root/reference does not exist on the GPU box), %d processes, 1 torch "
-                                       "thread each" % workers, "host_cores": os.cpu_count()},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": cpu_impl()[0],
+                             "sample": "%s; %d processes" % (cpu_impl_text(cpu_impl()[0]), workers), "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -282,7 +299,7 @@ def main():
         model = SimpleNN(board=(L, C)) if args.net == "simple" else ResNetZero(
             DotDict({"nn": {"model_parameters": resnet_zero_parameters((L, C))}}))
         if args.net_plan == "fused":
-            ev = (FusedSimpleNN if args.net == "simple" else FusedResNetZero)(model, eng, dtype=dt)
+            ev = FusedSimpleNN(model, eng, dtype=dt) if args.net == "simple" else FusedResNetZero(model, eng, dtype=dt, use_tower=not args.no_tower)
         else:
             ev = DeviceEvaluator(model, eng, dtype=dt, channels_last=True)
 
@@ -482,8 +499,12 @@ def main():
         eng_sp = engine.Engine((L, C), n_games=sp_games, max_nodes=sp_nodes, device=dev, eval_cache=use_cache)
         eng_sp.set_mode(False, args.max_inline)
         eng_sp.LADDER_STEPS = args.ladder_steps
-        ev_sp = (FusedSimpleNN if args.net == "simple" else FusedResNetZero)(model, eng_sp, dtype=dt) if args.net_plan == "fused" \
-            else DeviceEvaluator(model, eng_sp, dtype=dt, channels_last=True)
+        if args.net_plan != "fused":
+            ev_sp = DeviceEvaluator(model, eng_sp, dtype=dt, channels_last=True)
+        elif args.net == "simple":
+            ev_sp = FusedSimpleNN(model, eng_sp, dtype=dt)
+        else:
+            ev_sp = FusedResNetZero(model, eng_sp, dtype=dt, use_tower=not args.no_tower)
         sp_params = DotDict({"self_play": {"reuse_mcts_tree": True, "noise": NOISE,
                                            "mcts": {"mcts_num_read": args.sims, "mcts_cpuct": (1.25, 19652),
                                                     "temperature": {0: 1.0, 12: 0.02}, "max_async_searches": 1}}})

@@ -12,6 +12,7 @@
 #include "dbaz_game_kernels.cuh"
 #include "dbaz_nn_kernels.cuh"
 #include "dbaz_tree_kernels.cuh"
+#include "dbaz_tower.cuh"
 
 using namespace dbaz;
 
@@ -27,6 +28,8 @@ struct dbaz_engine {
     int pending;          // max_pending_evals of the current search
     int cache_log2;       // log2(entries) of the eval cache, 0 = none
     unsigned long long* d_status;
+    int* d_tower_err;     // set by k_resnet_tower when a barrier wait times out
+    long long* tower_dbg; // caller-owned timeline buffer (dbaz_nn_tower_trace), may be null
     std::string err;
 };
 
@@ -245,6 +248,7 @@ void dbaz_engine_destroy(dbaz_engine* e) {
     cudaFree(e->ta.ctr);
     cudaFree(e->ta.cache);
     cudaFree(e->d_status);
+    cudaFree(e->d_tower_err);
     delete e;
 }
 
@@ -419,6 +423,46 @@ int dbaz_nn_heads(dbaz_engine* e, const void* logits, int32_t ld, int32_t dtype,
     else if (dtype == DBAZ_F32) k_nn_heads<float><<<grid, 256, 0, S(stream)>>>((const float*)logits, ld, A, priors, values, n);
     else return fail(e, "bad dtype");
     return launch_ok(e, "k_nn_heads");
+}
+
+/* ---------------------------------------------------------- residual tower */
+
+int dbaz_nn_tower_geometry(dbaz_engine* e, int32_t* out8) {
+    if (!e || !out8) return 1;
+    const TowerGeom g = tower_geom(e->board.rows, e->board.cols);
+    out8[0] = g.ok; out8[1] = g.nb; out8[2] = g.plane; out8[3] = g.buf; out8[4] = TOWER_CHUNK_BYTES;
+    out8[5] = TOWER_CHUNKS_PER_STAGE; out8[6] = TOWER_C; out8[7] = g.WP;
+    return 0;
+}
+
+int dbaz_nn_tower_planarize(dbaz_engine* e, const void* nhwc, void* tiles, int64_t n, uint64_t stream) {
+    if (!e || !nhwc || !tiles) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    const std::string err = tower_planarize(tower_geom(e->board.rows, e->board.cols), nhwc, tiles, n, S(stream));
+    return err.empty() ? 0 : fail(e, err);
+}
+
+int dbaz_nn_tower(dbaz_engine* e, const void* tiles, const void* packed_w, const float* bias, int32_t n_stages, int32_t head_cout,
+                  void* out, int64_t n, uint64_t stream) {
+    if (!e || !tiles || !packed_w || !bias || !out) return 1;
+    if (n <= 0) return 0;
+    DeviceGuard guard(e->cfg.device);
+    if (!e->d_tower_err) {
+        DBAZ_CK(e, cudaMalloc(&e->d_tower_err, sizeof(int)));
+        DBAZ_CK(e, cudaMemset(e->d_tower_err, 0, sizeof(int)));
+    }
+    TowerLaunch a;
+    a.blob = tiles; a.packed_w = packed_w; a.bias = bias; a.out = out; a.n_stages = n_stages; a.head_cout = head_cout;
+    a.n_boards = n; a.n_sms = e->n_sms; a.err_flag = e->d_tower_err; a.dbg = e->tower_dbg;
+    const std::string err = tower_launch(tower_geom(e->board.rows, e->board.cols), a, S(stream));
+    return err.empty() ? 0 : fail(e, err);
+}
+
+int dbaz_nn_tower_trace(dbaz_engine* e, int64_t* timeline) {
+    if (!e) return 1;
+    e->tower_dbg = reinterpret_cast<long long*>(timeline);
+    return 0;
 }
 
 /* ---------------------------------------------------------------- search */

@@ -304,6 +304,35 @@ class Engine:
                                         self._stream()))
         return priors, values
 
+    # ------------------------------------------------- residual tower (tcgen05)
+    def tower_geometry(self):
+        """dict(ok, nb boards per tile, plane, tile_bytes, chunk_bytes, chunks_per_stage, channels, wp) of the fused
+        residual-tower kernel for this board (include/dbaz_b200.h: dbaz_nn_tower_geometry)."""
+        out = (C.c_int32 * 8)()
+        self.lib.dbaz_nn_tower_geometry(self._h, out)
+        keys = ("ok", "nb", "plane", "tile_bytes", "chunk_bytes", "chunks_per_stage", "channels", "wp")
+        return dict(zip(keys, list(out)))
+
+    def tower_tiles(self, n):
+        """Zero-filled planar tile buffer for up to n boards (pads must stay zero: allocate once, reuse)."""
+        g = self.tower_geometry()
+        n_tiles = -(-int(n) // g["nb"])
+        return torch.zeros((n_tiles, g["tile_bytes"]), dtype=torch.uint8, device=self.device)
+
+    def tower_planarize(self, nhwc, tiles):
+        """[n, L+1, C+1, 64] bf16 (contiguous NHWC) -> planar tiles, in place on `tiles`."""
+        n = nhwc.shape[0]
+        self._ck(self.lib.dbaz_nn_tower_planarize(self._h, _ptr(nhwc), _ptr(tiles), n, self._stream()))
+        return tiles
+
+    def tower(self, tiles, packed_w, bias, n_stages, head_cout, out):
+        """The residual tower (and, with head_cout, the fused 1x1 head conv + ReLU) over the boards in `tiles`;
+        out: [n, L+1, C+1, head_cout or 64] bf16 (include/dbaz_b200.h: dbaz_nn_tower)."""
+        n = out.shape[0]
+        self._ck(self.lib.dbaz_nn_tower(self._h, _ptr(tiles), _ptr(packed_w), _ptr(bias), int(n_stages), int(head_cout), _ptr(out), n,
+                                        self._stream()))
+        return out
+
     # -------------------------------------------------------------- search
     def reset_roots(self, states=None):
         """create_root_uct_node (mcts.py:156-160) for every tree."""

@@ -379,6 +379,46 @@ def _stem_mma_ok(conv, engine, dtype):
             and conv.kernel_size == (3, 3) and conv.in_channels == 3 and conv.out_channels % 64 == 0 and conv.out_channels <= 512)
 
 
+def tower_pack(w3, b3, w_head=None, b_head=None):
+    """Weights of the fused residual-tower kernel in the order include/dbaz_b200.h (dbaz_nn_tower) documents.
+    w3 float32 [S, 64, 64, 3, 3], b3 float32 [S, 64]: the S conv stages with their BatchNorm folded in;
+    w_head [hc, 64], b_head [hc]: the 1x1 head convolution (optional).  Returns (packed uint8 [bytes], bias float32 [S(+1), 64])."""
+    S = w3.shape[0]
+    assert tuple(w3.shape[1:]) == (64, 64, 3, 3)
+    x = w3.reshape(S, 64, 4, 2, 8, 3, 3).permute(0, 6, 2, 3, 5, 1, 4)      # [S, kx, ks, kh, ky, co, i]
+    x = torch.flip(x, dims=(4,)).reshape(S, 12, 2, 192, 8)                  # rows: ky = 2, 1, 0
+    parts = [x.to(torch.bfloat16).contiguous().view(torch.uint8).reshape(-1)]
+    bias = [b3.float()]
+    if w_head is not None:
+        hc = w_head.shape[0]
+        h = w_head.reshape(hc, 4, 2, 8).permute(1, 2, 0, 3)                 # [ks, kh, co, i]
+        parts.append(h.to(torch.bfloat16).contiguous().view(torch.uint8).reshape(-1))
+        bh = torch.zeros((1, 64), dtype=torch.float32, device=b3.device)
+        bh[0, :hc] = b_head.float()
+        bias.append(bh)
+    return torch.cat(parts).contiguous(), torch.cat(bias).contiguous()
+
+
+def tower_reference(x_nhwc, w3, b3, w_head=None, b_head=None):
+    """What the tower kernel computes, in plain PyTorch float32 on bf16-rounded weights, activations rounded to bf16
+    between stages (the kernel keeps them as bf16 in shared memory).  x_nhwc [n, H, W, 64]; returns NHWC bf16."""
+    r = lambda t: t.to(torch.bfloat16).float()
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    blk = mid = out = x
+    for s in range(w3.shape[0]):
+        y = F.conv2d(x if s % 2 == 0 else mid, r(w3[s]), b3[s].float(), padding=1)
+        if s % 2 == 0:
+            blk = x
+            mid = r(F.relu(y))
+            out = mid
+        else:
+            x = r(F.relu(y + blk))
+            out = x
+    if w_head is not None:
+        out = r(F.relu(F.conv2d(out, r(w_head)[:, :, None, None], b_head.float())))
+    return out.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
 class FusedSimpleNN:
     """Inference plan for SimpleNN (dots_boxes_nn.py:61-98), 9 kernels per batch instead of the module's ~45.
 
@@ -480,11 +520,15 @@ class FusedResNetZero:
     kernels per residual block.  The input BatchNorm folds into the stem tables (leaf gather + conv0 + ReLU from the
     packed leaf states, own kernel); both 1x1 head convs are one conv, both head FCs one GEMM."""
 
-    def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True):
+    def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True, use_tower=True):
         self.engine, self.dtype = engine, dtype
         dev = engine.device
         model = model.to(dev).train(False)
         cap = engine.n_games * engine.max_pending
+
+        def conv_fold(conv, bn):
+            s, t = _bn_affine(bn)
+            return conv.weight.detach().float() * s.view(-1, 1, 1, 1), conv.bias.detach().float() * s + t
 
         def conv_pack(conv, bn):
             if isinstance(conv, nn.Sequential):
@@ -518,6 +562,23 @@ class FusedResNetZero:
         vw, vb, _ = conv_pack(vh.conv0, vh.bn0)
         self.head_conv = (torch.cat([pw, vw], 0).contiguous(memory_format=torch.channels_last), torch.cat([pb, vb]))
         cp, cv = pw.shape[0], vw.shape[0]
+        # The whole tower (every residual block) and the two 1x1 head convolutions as ONE persistent tcgen05 kernel
+        # (csrc/dbaz_tower.cu): activations stay in shared memory across all convolutions, weights stream by TMA.
+        self.tower = None
+        blocks = list(model.resnet.resblocks)
+        if (use_tower and self.stem_mma is not None and dtype == torch.bfloat16 and engine.tower_geometry()["ok"] and len(blocks) > 0
+                and c0.out_channels == 64 and cp + cv in (16, 32)
+                and all(tuple(c.kernel_size) == (3, 3) and tuple(c.padding) == (1, 1) and c.in_channels == 64 and c.out_channels == 64 and c.groups == 1
+                        for b in blocks for c in (b.conv1, b.conv2))):
+            folded = [conv_fold(c, bn) for b in blocks for c, bn in ((b.conv1, b.bn1), (b.conv2, b.bn2))]
+            w3 = torch.stack([w for w, _ in folded])
+            b3 = torch.stack([b for _, b in folded])
+            pwf, pbf = conv_fold(ph.conv0, ph.bn0)
+            vwf, vbf = conv_fold(vh.conv0, vh.bn0)
+            packed, bias = tower_pack(w3, b3, torch.cat([pwf, vwf], 0).reshape(cp + cv, 64), torch.cat([pbf, vbf]))
+            self.tower = (packed, bias, w3.shape[0], cp + cv)
+            self.tower_tiles = engine.tower_tiles(cap)
+            self.tower_out = torch.empty((cap, engine.rows, engine.cols, cp + cv), dtype=dtype, device=dev)
         hw = engine.rows * engine.cols
         A, fi = engine.A, vh.fc0.out_features
         # one GEMM over the NHWC-flattened [hw, cp+cv] head activations: columns [0, A) policy logits, [A, A+fi) value hidden
@@ -531,7 +592,7 @@ class FusedResNetZero:
         self.A = A
         self.ld = (A + 1 + 7) // 8 * 8
         self.logits = torch.zeros((cap, self.ld), dtype=dtype, device=dev)
-        self.engine_launches = 2 if (self.fused_stem is not None or self.stem_mma is not None) else 1  # own kernels per batch
+        self.engine_launches = (2 if (self.fused_stem is not None or self.stem_mma is not None) else 1) + (2 if self.tower is not None else 0)  # own kernels per batch
         engine.set_planes(dtype, channels_last=True)
 
     @torch.no_grad()
@@ -545,11 +606,16 @@ class FusedResNetZero:
         else:
             w, b, pad = self.stem
             x = _conv_relu(eng.planes * self.in_scale + self.in_shift, w, b, pad)
-        for (w1, b1, p1), (w2, b2, p2) in self.blocks:
-            x = _conv_add_relu(_conv_relu(x, w1, b1, p1), w2, x, b2, p2)
-        hw_, hb = self.head_conv
-        h = _conv_relu(x, hw_, hb, (0, 0))
-        out = torch.addmm(self.head_b, h.permute(0, 2, 3, 1).reshape(n, -1), self.head_w)
+        if self.tower is not None:
+            packed, bias, n_stages, hc = self.tower
+            eng.tower_planarize(self.stem_out[:n], self.tower_tiles)
+            h = eng.tower(self.tower_tiles, packed, bias, n_stages, hc, self.tower_out[:n]).reshape(n, -1)
+        else:
+            for (w1, b1, p1), (w2, b2, p2) in self.blocks:
+                x = _conv_add_relu(_conv_relu(x, w1, b1, p1), w2, x, b2, p2)
+            hw_, hb = self.head_conv
+            h = _conv_relu(x, hw_, hb, (0, 0)).permute(0, 2, 3, 1).reshape(n, -1)
+        out = torch.addmm(self.head_b, h, self.head_w)
         logits = self.logits[:n]
         logits[:, :self.A] = out[:, :self.A]
         logits[:, self.A:self.A + 1] = torch.addmm(self.v_b, F.relu(out[:, self.A:]), self.v_w)

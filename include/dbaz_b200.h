@@ -214,6 +214,31 @@ int dbaz_nn_stem_mma(dbaz_engine *e, const dbaz_state *leaf_states, const void *
 int dbaz_nn_heads(dbaz_engine *e, const void *logits, int32_t ld, int32_t dtype, float *priors, float *values, int64_t n,
                   uint64_t stream);
 
+/* ---- residual tower of ResNetZero as ONE persistent tcgen05 kernel (dotsboxesaz_b200/csrc/dbaz_tower.cu) ----
+ * Replaces the 2 * nb_blocks conv3x3 -> BatchNorm -> ReLU (-> +x) library calls of ResNet.forward / ResBlock.forward
+ * (nn.py:16-30,33-58; 20 blocks of 64 channels in configuration.py:133-155) and, optionally, the two 1x1 head
+ * convolutions + BatchNorm + ReLU (PolicyHead / ValueHead conv0, nn.py:80,95).  64 channels, boards with L + 1 <= 6.
+ *
+ * dbaz_nn_tower_geometry: out8 = {supported, boards per tile, plane bytes, tile bytes, weight chunk bytes (6144),
+ *   chunks per stage (12), channels (64), padded row width C + 2}.
+ * Activations enter as "planar tiles" (tile t = boards [t * nb, (t + 1) * nb)): tile_bytes per tile, byte
+ *   128 + cg * plane + ((h * 128) + b * (C + 2) + w) * 16 + 2 * (c % 8)  holds channel c = 8 cg + c % 8 of point (h, w) of
+ *   board b of the tile; every other byte must be zero (allocate zero-filled once; dbaz_nn_tower_planarize writes only
+ *   real points).  dbaz_nn_tower_planarize converts [n][L+1][C+1][64] bf16 (NHWC).
+ * packed_w: for stage s (conv1 / conv2 of block s / 2, BatchNorm folded into weight and bias) 12 chunks
+ *   p = 4 * kx + ks of 6144 bytes [kh 2][row = 64 * (2 - ky) + cout][8] bf16 = weight[cout][16 ks + 8 kh + i][ky][kx];
+ *   then, if head_cout, one chunk [ks 4][kh 2][cout][8] of the 1x1 head weights.  bias float32[n_stages (+1)][64].
+ * out: [n][L+1][C+1][head_cout ? head_cout : 64] bf16 = relu(head(tower(x))) resp. tower(x).
+ * Stage s odd adds the input of stage s - 1 (the residual) before the ReLU.  head_cout in {0, 16, 32}. */
+int dbaz_nn_tower_geometry(dbaz_engine *e, int32_t *out8);
+int dbaz_nn_tower_planarize(dbaz_engine *e, const void *nhwc, void *tiles, int64_t n, uint64_t stream);
+int dbaz_nn_tower(dbaz_engine *e, const void *tiles, const void *packed_w, const float *bias, int32_t n_stages,
+                  int32_t head_cout, void *out, int64_t n, uint64_t stream);
+/* Diagnostics: later dbaz_nn_tower() launches record a clock64 timeline of CTA 0's first tile into timeline
+ * (device int64[64][16]: per stage {MMA: stage start, weights of pass 0 / 1 landed, last MMA issued; epilogue of
+ * h-block h: accumulator ready, block written}); NULL switches it off. */
+int dbaz_nn_tower_trace(dbaz_engine *e, int64_t *timeline);
+
 /* ---- test/bench utility: deterministic stand-in for the policy/value net ----
  * (SURVEY.md 8a KAT definition; kind 0 hash-seeded, kind 1 uniform prior) over leaf_states[n]. */
 int dbaz_fake_nn(dbaz_engine *e, const dbaz_state *leaf_states, float *priors, float *values, int32_t kind,

@@ -2,7 +2,8 @@
 engine's fused epilogue / heads kernels) against the plain PyTorch fp32 modules in eval mode.
 Tolerances: fp32 plan 2e-5 abs on probabilities/values (north_star: Q/priors within 1e-5 relative is
 for the TREE given identical net outputs; the net itself is floating point and its plan re-associates
-sums); bf16 plan 3e-2 abs (bf16 has 8 mantissa bits)."""
+sums); bf16 plans: BF16_BOUNDS below (relative error of every prior above 1e-3, per-row KL, tanh value) against the
+fp32 module on bf16-rounded weights."""
 import numpy as np
 import pytest
 
@@ -20,8 +21,55 @@ def _randomise_bn(model, seed):
             m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.2)
 
 
-@pytest.mark.parametrize("net,board", [("simple", (3, 3)), ("simple", (5, 5)), ("resnet", (3, 3)), ("resnet", (5, 5))])
-def test_fused_plans_match_torch_modules(net, board):
+def _rounded_copy(model, dtype):
+    """The fp32 module with every conv / linear weight rounded to `dtype` (what a 16-bit plan can represent at best)."""
+    import copy
+    m = copy.deepcopy(model)
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear)):
+                mod.weight.copy_(mod.weight.to(dtype).float())
+    return m
+
+
+def _net_errors(p, v, p_ref, v_ref):
+    """max relative error over every prior above 1e-3, largest per-row KL(ref || p), max |v - v_ref|, max abs prior error."""
+    big = p_ref > 1e-3
+    rel = ((p - p_ref).abs() / p_ref)[big].max().item()
+    kl = (p_ref * (torch.log(p_ref.clamp_min(1e-30)) - torch.log(p.clamp_min(1e-30)))).sum(1).max().item()
+    return {"rel": rel, "kl": kl, "v": (v - v_ref).abs().max().item(), "abs": (p - p_ref).abs().max().item()}
+
+
+def _record(name, errs):
+    """Achieved errors go to gpurun_out/net_errors.json (scratch) so that the bounds below can be read against them."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "net_errors.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        d = json.load(open(path)) if os.path.exists(path) else {}
+        d[name] = errs
+        json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+# bf16 bounds per net, every one about 3x what the plans achieve on a B200 (profiles/r02_net_errors.md; BatchNorm
+# statistics and weights are random here, which makes the nets far more sensitive than trained ones): relative error of
+# every prior above 1e-3, per-row KL divergence, tanh value.  A wrong fold of one BatchNorm moves the KL by orders of magnitude.
+BF16_BOUNDS = {("simple", 3): {"rel": 1.5e-2, "kl": 1e-5, "v": 8e-3}, ("simple", 5): {"rel": 1.5e-2, "kl": 1e-5, "v": 8e-3},
+               ("resnet", 3): {"rel": 1e-1, "kl": 3e-4, "v": 2e-2}, ("resnet", 5): {"rel": 3e-1, "kl": 2.5e-3, "v": 5e-2}}
+# the plain bf16 module (no fused plan) exponentiates a bf16 log_softmax: looser
+MODULE_BOUNDS = {"rel": 1.5e-1, "kl": 2e-2, "v": 3e-2}
+
+
+@pytest.mark.parametrize("net,board,blocks", [("simple", (3, 3), 0), ("simple", (5, 5), 0), ("resnet", (3, 3), 4), ("resnet", (5, 5), 4),
+                                              ("resnet", (3, 3), 20), ("resnet", (5, 5), 20)])
+def test_fused_plans_match_torch_modules(net, board, blocks):
+    """fp32 plan: 2e-5 abs against the fp32 module.  bf16 plans: against the fp32 module evaluated on bf16-rounded
+    weights -- a relative bound on every prior above 1e-3, a per-row KL bound and an absolute bound on the tanh value
+    (BF16_BOUNDS); ResNetZero also at its full depth of 20 blocks (configuration.py:133-155), with the tcgen05 tower
+    kernel and with the library convolutions."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from dotsboxesaz_b200 import engine
@@ -37,7 +85,7 @@ def test_fused_plans_match_torch_modules(net, board):
         model = SimpleNN(board=board)
         plan_cls = FusedSimpleNN
     else:
-        model = ResNetZero(DotDict({"nn": {"model_parameters": resnet_zero_parameters(board, nb_blocks=4)}}))
+        model = ResNetZero(DotDict({"nn": {"model_parameters": resnet_zero_parameters(board, nb_blocks=blocks)}}))
         plan_cls = FusedResNetZero
     _randomise_bn(model, 2)
     model = model.cuda().eval()
@@ -51,30 +99,53 @@ def test_fused_plans_match_torch_modules(net, board):
     x32 = eng.features(st, torch.float32)
     with torch.no_grad():
         logp, v = model(x32)
-    p_ref, v_ref = torch.exp(logp), v.reshape(-1)
-    for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 3e-2)):
+        logp16, v16 = _rounded_copy(model, torch.bfloat16)(x32)
+    refs = {torch.float32: (torch.exp(logp), v.reshape(-1)), torch.bfloat16: (torch.exp(logp16), v16.reshape(-1))}
+    tag = "%s-%dx%d-%d" % (net, board[0], board[1], blocks)
+
+    def check(name, dtype):
+        torch.cuda.synchronize()
+        p_ref, v_ref = refs[dtype]
+        assert torch.isfinite(eng.priors).all()
+        # the plans' heads kernel normalises in float32; the plain bf16 module exponentiates a bf16 log_softmax
+        assert (eng.priors.sum(1) - 1).abs().max() < (1e-3 if name.startswith("plan") else 1e-2)
+        errs = _net_errors(eng.priors, eng.values, p_ref, v_ref)
+        _record("%s %s" % (tag, name), errs)
+        if dtype == torch.float32:
+            assert errs["abs"] < 2e-5 and errs["v"] < 2e-5, (tag, name, errs)
+        else:
+            bounds = BF16_BOUNDS[(net, board[0])] if name.startswith("plan") else MODULE_BOUNDS
+            for k, bound in bounds.items():
+                assert abs(errs[k]) < bound, (tag, name, k, errs)
+
+    for dtype in (torch.float32, torch.bfloat16):
+        dn = "fp32" if dtype == torch.float32 else "bf16"
         plan = plan_cls(model, eng, dtype=dtype)
         eng.planes.copy_(x32.to(dtype))
         eng.leaf_states.copy_(st)
         plan(eng)
-        torch.cuda.synchronize()
-        assert torch.isfinite(eng.priors).all()
-        assert (eng.priors.sum(1) - 1).abs().max() < 1e-3
-        assert (eng.priors - p_ref).abs().max().item() < tol, (net, board, dtype, (eng.priors - p_ref).abs().max().item())
-        assert (eng.values - v_ref).abs().max().item() < tol * (1 if dtype == torch.float32 else 3)
-        if dtype != torch.float32:  # the library-conv0 and the CUDA-core-stem variants of the same plan must agree as well
+        check("plan " + dn, dtype)
+        if dtype != torch.float32:
             assert plan.stem_mma is not None  # the default stem is the tensor-core kernel
-            for variant in (False, "fma"):
-                plan2 = plan_cls(model, eng, dtype=dtype, use_stem=variant)
-                assert plan2.stem_mma is None
-                eng.planes.copy_(x32.to(dtype))
-                plan2(eng)
-                assert (eng.priors - p_ref).abs().max().item() < tol, variant
-        # the un-fused evaluator (plain module on the same planes) must agree too
-        ev = DeviceEvaluator(model, eng, dtype=dtype, channels_last=True)
-        eng.planes.copy_(x32.to(dtype))
-        ev(eng)
-        assert (eng.priors - p_ref).abs().max().item() < tol
+            if net == "resnet":
+                assert plan.tower is not None  # ... and the default tower the tcgen05 kernel
+                plan_lib = plan_cls(model, eng, dtype=dtype, use_tower=False)
+                assert plan_lib.tower is None
+                plan_lib(eng)
+                check("plan bf16, library convolutions", dtype)
+            if blocks <= 4:  # the library-conv0 and the CUDA-core-stem variants of the same plan must agree as well
+                for variant in (False, "fma"):
+                    plan2 = plan_cls(model, eng, dtype=dtype, use_stem=variant)
+                    assert plan2.stem_mma is None
+                    eng.planes.copy_(x32.to(dtype))
+                    plan2(eng)
+                    check("plan bf16, stem %s" % variant, dtype)
+        if blocks <= 4:
+            # the un-fused evaluator (plain module on the same planes) must agree too
+            ev = DeviceEvaluator(model, eng, dtype=dtype, channels_last=True)
+            eng.planes.copy_(x32.to(dtype))
+            ev(eng)
+            check("module " + dn, dtype)
     eng.close()
 
 
