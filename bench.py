@@ -464,7 +464,7 @@ def main():
             # the library kernels the net picks at another batch size
             step_resident()
             vis_adaptive = visits.clone()
-            eng._ladder = lambda: [eng.n_games]
+            eng._ladder = lambda evaluator=None: [eng.n_games]
             step_resident()
             vis_full = visits.clone()
             del eng._ladder

@@ -432,8 +432,19 @@ class Engine:
     UNDERSIZE_GAIN = 1.05    # ... if it serves this much more rows per microsecond than the best batch that holds them
     WAVE_OVERHEAD_US = 40.0  # per-wave cost that does not depend on the batch (step kernel), for the same trade-off
 
-    def _ladder(self):
+    def _ladder(self, evaluator=None):
+        """Evaluator batch sizes of the adaptive loop, largest first.  An evaluator whose cost is a step function of
+        the batch with a known period (`batch_quantum`: the tower kernel runs boards-per-tile x SMs boards per
+        wave of its persistent grid) gets rungs at whole multiples of it."""
         n, steps = self.n_games, max(1, int(self.LADDER_STEPS))
+        q = int(getattr(evaluator, "batch_quantum", 0) or 0)
+        if q >= 64 and n >= q:
+            rows = {n} | {q * k for k in range(1, n // q + 1)}
+            r = q
+            while r > 64:
+                r //= 2
+                rows.add(max(64, -(-r // 8) * 8))
+            return sorted(rows, reverse=True)
         rows = {n}
         for k in range(1, steps + 1):
             rows.add(min(n, max(64, -(-(n * k // steps) // 8) * 8)))
@@ -457,7 +468,7 @@ class Engine:
                 self._noise_buf = torch.zeros((self.n_games, self.A), dtype=torch.float64, device=self.device)
             self._noise_buf.copy_(torch.as_tensor(noise, dtype=torch.float64).reshape(self.n_games, self.A))
             noise = self._noise_buf
-        ladder = self._ladder()
+        ladder = self._ladder(evaluator)
         per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
         graphs = self._ladder_graphs(evaluator, graph_waves, noise, coeff)
         self.begin(num_reads, noise, coeff, 1)
@@ -494,10 +505,10 @@ class Engine:
         """{batch rows: CUDA graph of `graph_waves` [step -> evaluator] waves} for every rung of the ladder (compact mode).
         Every batch size is captured up front: capturing re-binds the search head and idles all trees."""
         key = (id(evaluator), graph_waves, noise is not None, float(coeff), self._plane_cfg, 1, self._mode_key(), "ladder", self.LADDER_STEPS,
-               short_tail)
+               short_tail, tuple(self._ladder(evaluator)))
         if key not in self._graphs:
             graphs = {}
-            for rows in self._ladder():
+            for rows in self._ladder(evaluator):
                 self._batch_rows = rows
                 try:
                     graphs[rows] = self._capture(evaluator, self._rung_waves(rows, graph_waves) if short_tail else graph_waves, noise, coeff, 1)

@@ -577,6 +577,8 @@ class FusedResNetZero:
             vwf, vbf = conv_fold(vh.conv0, vh.bn0)
             packed, bias = tower_pack(w3, b3, torch.cat([pwf, vwf], 0).reshape(cp + cv, 64), torch.cat([pbf, vbf]))
             self.tower = (packed, bias, w3.shape[0], cp + cv)
+            # one wave of the tower's persistent grid: the adaptive wave loop puts its batch sizes at multiples of it
+            self.batch_quantum = engine.tower_geometry()["nb"] * engine.n_sms
             self.tower_tiles = engine.tower_tiles(cap)
             self.tower_out = torch.empty((cap, engine.rows, engine.cols, cp + cv), dtype=dtype, device=dev)
         hw = engine.rows * engine.cols

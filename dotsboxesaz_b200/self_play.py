@@ -278,7 +278,8 @@ class BatchedSelfPlay:
         info = eng.status()  # the only host synchronisation of the whole batch of games
         self.total_sims = info["sims"]
         self._device_hist = dict(states=hist_states, visits=hist_visits, active=hist_active, moves=hist_moves, stats=hist_stats,
-                                 q=hist_q, final=final, result=res, games_idxs=games_idxs, with_features=with_features)
+                                 q=hist_q, final=final, result=res, games_idxs=games_idxs, with_features=with_features,
+                                 noise=noise_all)  # the pre-drawn Dirichlet samples [move, game, A]: a run can be replayed
         return info
 
     def play_games_async(self, games_idxs, seed=0, start_states=None, with_features=True):
@@ -335,7 +336,7 @@ class BatchedSelfPlay:
         noise_buf = eng._noise_buf
         noise_arg = noise_buf if alpha > 0 else None  # alpha <= 0: the reference mixes the scalar 0.0 in (float32 arithmetic)
         graphs = eng._ladder_graphs(self.ev, self.graph_waves, noise_arg, coeff, short_tail=False)  # a small batch is no tail here
-        ladder = eng._ladder()
+        ladder = eng._ladder(self.ev)
         per_wave = 1 + int(getattr(self.ev, "engine_launches", 0))
 
         def start(restart):
@@ -418,7 +419,8 @@ class BatchedSelfPlay:
         self.total_sims = info["sims"]
         self._device_hist = dict(states=list(h_states.unbind(0)), visits=list(h_visits.unbind(0)), active=list(h_active.unbind(0)),
                                  moves=list(h_moves.unbind(0)), stats=list(h_stats.unbind(0)), q=list(h_q.unbind(0)), final=final,
-                                 result=res, games_idxs=games_idxs, with_features=with_features)
+                                 result=res, games_idxs=games_idxs, with_features=with_features,
+                                 noise=noise_all if alpha > 0 else None)  # pre-drawn Dirichlet samples [move, game, A]
         return info
 
     def device_samples(self):

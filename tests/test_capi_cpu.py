@@ -117,6 +117,16 @@ def test_adaptive_ladder_and_default_cache_size():
         for busy in (1, n // 3, n - 1, n):                        # every busy count has a rung that holds it
             assert min(r for r in lad if r >= busy) >= busy
 
+    # an evaluator with a batch quantum (the tower kernel: boards per tile x SMs) gets rungs at its multiples
+    class Ev:
+        batch_quantum = 2664
+    e.n_games, e.LADDER_STEPS = 16384, 16
+    lad = e._ladder(Ev())
+    assert lad[0] == 16384 and lad[1:7] == [15984, 13320, 10656, 7992, 5328, 2664] and min(lad) == 64
+    assert lad == sorted(set(lad), reverse=True) and all(r % 8 == 0 for r in lad)
+    e.n_games = 1000                                              # fewer games than one quantum: the plain ladder
+    assert e._ladder(Ev()) == e._ladder()
+
     class G33:
         BOARD_DIM = (3, 3)
 
