@@ -18,6 +18,9 @@ EMPTIED at the start of every step, inside the timed region.  Keys of the line b
   cpu_baseline   the real reference (oracle/_ref, staged by oracle/make_ref.sh; oracle/py_port.py if absent) on the host cores, bounded sample (N=1 only)
   ablation       the same step with the eval cache switched off, and whether the visit counts agree
   selfplay       whole self-play games per hour (`--selfplay-games` concurrent games per GPU, samples to the host)
+  configs        (N = 1) bounded sub-runs of BASELINE's other configurations and modes: configs[2] (5x5 x 2^20 random
+                 rollouts, plies/s), configs[3] (5x5 x 16384 games x 800 sims, ResNetZero bf16 with the tcgen05 tower
+                 kernel), max_pending_evals = 64 (the reference's shipped mode), SimpleNN in IEEE fp32 and TF32
 """
 import argparse
 import json
@@ -69,6 +72,10 @@ def parse_args():
                     help="async: every game at its own pace (BatchedSelfPlay.play_games_async); lockstep: all games move together")
     ap.add_argument("--selfplay-games", type=int, default=32768,
                     help="concurrent games per GPU of the games/hour measurement (the sims/s workload stays at --games)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the `configs` key: BASELINE configs[2] (5x5 random rollouts), configs[3] (5x5 x 16384 x 800, ResNetZero), "
+                         "the max_pending_evals = 64 mode and the fp32 / TF32 nets (bounded sub-runs, N = 1 only)")
+    ap.add_argument("--tf32", action="store_true", help="with --net-dtype fp32: allow TF32 tensor-core math (off: IEEE fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="processes for the CPU baseline (0 = min(cores-1, 64))")
     ap.add_argument("--cpu-positions", type=int, default=2, help="searches per worker in the bounded CPU sample")
@@ -231,6 +238,165 @@ def host_noise(rs, valid_np, alpha):
     return rs.dirichlet(np.ones(A) * alpha, size=valid_np.shape[0]) * valid_np  # mcts.py:220-223
 
 
+def sub_bench(extra, timeout=420):
+    """One bounded sub-run of this script (its own process: its own engine, graphs and HBM), parsed JSON line or error."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--no-cpu-baseline", "--no-ablation", "--no-selfplay",
+           "--no-configs"] + extra
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout, env=env, text=True)
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+        if out.returncode != 0 or not lines:
+            return {"error": "rc=%d %s" % (out.returncode, out.stderr[-300:])}
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001 -- a failed sub-run must not lose the main line
+        return {"error": repr(e)}
+
+
+def pick(d, roof_keys=("kernel", "achieved", "peak", "unit", "frac", "kernel_us", "share_of_step", "algorithmic_bytes_per_sim",
+                       "sims_per_launch", "launches_per_step", "cache_hit_frac", "terminal_leaf_frac", "mean_path_nodes")):
+    """The part of a sub-run's line the `configs` key keeps."""
+    if "error" in d:
+        return d
+    out = {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "dtype")}
+    out["e2e"] = (d.get("e2e") or {}).get("value")
+    out["workload"] = (d.get("config") or {}).get("workload")
+    if d.get("roofline"):
+        out["roofline"] = {k: d["roofline"].get(k) for k in roof_keys}
+    if d.get("roofline_net"):
+        out["roofline_net"] = {k: d["roofline_net"].get(k) for k in ("kernel", "achieved", "peak", "unit", "frac", "us_per_batch")}
+    return out
+
+
+def rollout_config(torch, dev, n=1 << 20, board=(5, 5)):
+    """BASELINE configs[2]: uniformly random legal playouts of `n` concurrent 5x5 games to the end (Philox4x32-10, one
+    thread per game, the whole game in registers).  plies/s with CUDA events over 5 launches on fresh states; the HBM
+    figure uses SURVEY 8d's 32 bytes per ply -- the kernel is bound by integer issue, not by HBM (profiles/)."""
+    from dotsboxesaz_b200 import engine
+    eng = engine.Engine(board, n_games=8, max_nodes=16, device=dev)
+    try:
+        fresh = eng.new_states(n)
+        st = fresh.clone()
+        plies = eng.random_rollout(st, seed=0)
+        torch.cuda.synchronize()
+        total = int(plies.sum())
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = 0.0
+        reps = 5
+        for r in range(reps):
+            st.copy_(fresh)
+            a.record()
+            eng.random_rollout(st, seed=0)
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        sec = ms / reps / 1e3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        gbs = total * 32 / sec / 1e9
+        # host-to-host: packed states from pinned memory, final states and ply counts back
+        host_in = fresh.cpu().pin_memory()
+        host_out = torch.empty_like(host_in).pin_memory()
+        plies_out = torch.empty((n,), dtype=torch.int32).pin_memory()
+        t0 = time.time()
+        st.copy_(host_in, non_blocking=True)
+        pl = eng.random_rollout(st, seed=0)
+        host_out.copy_(st, non_blocking=True)
+        plies_out.copy_(pl, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_sec = time.time() - t0
+        out = {"metric": "random_rollout_plies_per_sec", "value": total / sec, "unit": "plies/s", "games_per_sec": n / sec,
+               "games": n, "plies_per_game": total / n, "ms_per_launch": sec * 1e3, "gpu_launches": 1,
+               "e2e": total / e2e_sec, "e2e_h2d_d2h_bytes": int(host_in.numel() * 8 * 2 + n * 4),
+               "workload": "%dx%d boxes, %d concurrent games, uniformly random legal moves to the end (BASELINE configs[2])" % (board[0], board[1], n),
+               "roofline": {"bound": "hbm", "kernel": "k_game_rollout", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                            "algorithmic_bytes_per_ply": 32, "note": "integer-issue bound: one thread plays a whole game in registers, HBM sees each state once in and once out"}}
+    finally:
+        eng.close()
+    # the reference's BoxesState on one host core, bounded sample
+    try:
+        kind, impl = cpu_impl()
+        if kind == "reference":
+            p, sec_cpu = impl.worker_rollouts((board, 200, 0))
+            out["cpu_baseline"] = {"value": p / sec_cpu, "unit": "plies/s", "cores": 1, "kind": "reference",
+                                   "sample": "200 random 5x5 playouts with the reference's BoxesState.play_ (oracle/_ref), 1 process"}
+    except Exception as e:  # noqa: BLE001
+        out["cpu_baseline"] = {"error": repr(e)}
+    return out
+
+
+def coach_config(args, torch, dist, rank, world, dev, board=(5, 5), games_per_rank=1024, sims=200):
+    """BASELINE configs[4]: full coach iterations (self-play + NCCL sample gather + train + NCCL weight broadcast), 5x5,
+    ResNetZero (20 blocks), games sharded over the ranks.  Generations 0 and 1 (generation 0 trains 0 epochs -- the
+    reference's min(2 * generation, nb_epochs), nn.py:205 -- generation 1 trains one).  Bounded: 1024 games per rank at
+    200 sims/move, at most 65536 training positions."""
+    import copy
+    import tempfile
+    import shutil
+    from dotsboxesaz_b200 import coach, configuration
+    from dotsboxesaz_b200.dots_boxes.dots_boxes_game import BoxesState
+    from dotsboxesaz_b200.nn import resnet_zero_parameters
+    BoxesState.init_static_fields((board,))
+    params = copy.deepcopy(configuration.resnet)
+    params.nn.model_parameters = resnet_zero_parameters(board, nb_blocks=20)
+    root = tempfile.mkdtemp(prefix="dbaz_coach_") if rank == 0 else None
+    box = [root]
+    dist.broadcast_object_list(box, src=0)
+    root = box[0]
+    params.rewrite_str("data/_exp_", root)
+    params.self_play.num_games = games_per_rank * world
+    params.self_play.concurrent_games = games_per_rank
+    params.self_play.max_nodes_per_tree = 4096
+    params.self_play.mcts.mcts_num_read = sims
+    params.self_play.export_frames = False
+    params.nn.pytorch_device = "cuda:%d" % torch.cuda.current_device()
+    params.nn.train_params.nb_epochs = 1
+    params.nn.train_params.train_batch_size = 1024
+    params.nn.train_params.val_batch_size = 1024
+    params.nn.train_params.max_samples_per_gen = 65536
+    t0 = time.time()
+    try:
+        timings = coach.learn_to_play(params, 0, 1)
+    finally:
+        BoxesState.init_static_fields(((3, 3),))
+        if rank == 0:
+            shutil.rmtree(root, ignore_errors=True)
+    if rank != 0:
+        return None
+    g1 = timings[-1]
+    return {"workload": "%dx%d boxes, ResNetZero 20 blocks bf16, %d games/generation (%d per GPU) at %d sims/move, generations 0-1, "
+                        "samples gathered with NCCL, rank 0 trains, weights broadcast with NCCL (BASELINE configs[4])"
+                        % (board[0], board[1], games_per_rank * world, games_per_rank, sims),
+            "n_gpus": world, "total_s": time.time() - t0, "generations": timings,
+            "selfplay_games_per_hour": games_per_rank * world / max(g1.get("play_s", 1e-9), 1e-9) * 3600.0,
+            "gather_s": g1.get("gather_s"), "train_s": g1.get("train_s"), "broadcast_s": g1.get("broadcast_s"), "rows": g1.get("rows")}
+
+
+def other_configs(args, torch, dev):
+    """BASELINE.json configs beyond the headline and the modes the verdict asked for, each as a bounded sub-run."""
+    out = {}
+    try:
+        out["configs2_rollouts_5x5_1M"] = rollout_config(torch, dev)
+    except Exception as e:  # noqa: BLE001
+        out["configs2_rollouts_5x5_1M"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    out["configs3_5x5_16384games_800sims_resnet_bf16"] = pick(sub_bench(
+        ["--board", "5x5", "--net", "resnet", "--games", "16384", "--sims", "800", "--steps", "2", "--warmup", "3", "--eval-cache", "22"]))
+    out["max_pending_evals_64_3x3_4096games"] = pick(sub_bench(
+        ["--board", "3x3", "--net", "simple", "--games", "4096", "--sims", "800", "--pending", "64", "--steps", "2", "--warmup", "3"]))
+    out["net_fp32_ieee_3x3_4096games"] = pick(sub_bench(
+        ["--board", "3x3", "--net", "simple", "--games", "4096", "--sims", "800", "--net-dtype", "fp32", "--steps", "1", "--warmup", "3"]))
+    out["net_tf32_3x3_4096games"] = pick(sub_bench(
+        ["--board", "3x3", "--net", "simple", "--games", "4096", "--sims", "800", "--net-dtype", "fp32", "--tf32", "--steps", "1", "--warmup", "3"]))
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -281,6 +447,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -543,10 +711,40 @@ def main():
                             "samples copied to the host inside the timed region"
                             % (sp_games, "every game at its own pace" if args.selfplay_mode == "async" and adaptive else "all games move by move")}
 
+    coach_info = None
+    if world > 1 and not args.no_configs:
+        # BASELINE configs[4]: full coach iterations on N GPUs (every rank takes part)
+        for name in ("eng_sp", "eng"):
+            obj = locals().get(name)
+            if obj is not None:
+                try:
+                    obj.close()
+                except Exception:
+                    pass
+        torch.cuda.empty_cache()
+        try:
+            coach_info = coach_config(args, torch, dist, rank, world, dev)
+        except Exception as e:  # noqa: BLE001 -- must not lose the main line
+            coach_info = {"error": repr(e)}
+
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        # free this process's engines first: the sub-runs need the HBM
+        for name in ("eng_sp", "ev_sp", "eng", "ev"):
+            obj = locals().get(name)
+            if name.startswith("eng") and obj is not None:
+                try:
+                    obj.close()
+                except Exception:
+                    pass
+        torch.cuda.empty_cache()
+        configs = other_configs(args, torch, dev)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64 PUCT over f32/i32 node stats; net %s" % (args.net_dtype if args.net != "fake" else "none (fake)"),
+                "dtype": "f64 PUCT over f32/i32 node stats; net %s" % (
+                    ("tf32" if (args.tf32 and args.net_dtype == "fp32") else args.net_dtype) if args.net != "fake" else "none (fake)"),
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "board": args.board, "games_per_gpu": args.games,
                            "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "net_plan": args.net_plan, "max_pending_evals": args.pending,
@@ -560,7 +758,8 @@ def main():
                         "h2d_bytes_per_step": int(roots_host.numel() * 8 + noise_pool[0].numel() * 8),
                         "d2h_bytes_per_step": int(visits_host.numel() * 4),
                         "api": "Engine.reset_roots(host roots) + Engine.run_search(host Dirichlet noise) + root_visits -> host"},
-                "gpu_launches": launches, "roofline": roof, "roofline_net": net_roof, "cpu_baseline": cpu, "clocks": clocks, "ablation": ablation}
+                "gpu_launches": launches, "roofline": roof, "roofline_net": net_roof, "cpu_baseline": cpu, "clocks": clocks, "ablation": ablation,
+                "configs": configs, "coach": coach_info}
         if c_rate is not None:
             line["cpu_c_oracle_1core_sims_per_sec"] = c_rate
         emit(line)

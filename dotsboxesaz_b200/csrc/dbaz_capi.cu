@@ -115,7 +115,7 @@ static int launch_stem(dbaz_engine* e, const dbaz_state* leaves, const float* w0
 }
 
 template <typename T, int NT>
-static int launch_stem_mma_nt(dbaz_engine* e, const dbaz_state* leaves, const T* w48, T* out, int64_t n, int cout, cudaStream_t st) {
+static int launch_stem_mma_nt(dbaz_engine* e, const dbaz_state* leaves, const T* w48, T* out, int64_t n, int cout, cudaStream_t st, StemPlanar pl) {
     const int H = e->board.rows, W = e->board.cols, HW = H * W;
     const size_t smem = (size_t)(cout / 8) * 3 * 32 * sizeof(uint2) + (size_t)((HW * STEM_K + 15) & ~15) +
                         (size_t)STEM_WARPS * 16 * (8 * (NT >= 16 ? NT / 2 : NT) * 2 + 16);
@@ -124,16 +124,17 @@ static int launch_stem_mma_nt(dbaz_engine* e, const dbaz_state* leaves, const T*
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((items + STEM_WARPS - 1) / STEM_WARPS, (int64_t)e->n_sms * resident));
     cudaError_t rc = cudaFuncSetAttribute(k_nn_stem_mma<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_nn_stem_mma)", rc);
-    k_nn_stem_mma<T, NT><<<grid, STEM_WARPS * 32, smem, st>>>(leaves, w48, out, (int)n, cout, H, W);
+    k_nn_stem_mma<T, NT><<<grid, STEM_WARPS * 32, smem, st>>>(leaves, w48, out, (int)n, cout, H, W, pl);
     return launch_ok(e, "k_nn_stem_mma");
 }
 
 template <typename T>
-static int launch_stem_mma(dbaz_engine* e, const dbaz_state* leaves, const T* w48, T* out, int64_t n, int cout, cudaStream_t st) {
+static int launch_stem_mma(dbaz_engine* e, const dbaz_state* leaves, const T* w48, T* out, int64_t n, int cout, cudaStream_t st,
+                           StemPlanar pl = StemPlanar{0, 0, 0, 0}) {
     // one work item = 16 rows x (8 * NT) channels; all channels in one item when cout <= 256 (A fragments built once)
-    if (cout % 256 == 0) return launch_stem_mma_nt<T, 32>(e, leaves, w48, out, n, cout, st);
-    if (cout % 128 == 0) return launch_stem_mma_nt<T, 16>(e, leaves, w48, out, n, cout, st);
-    return launch_stem_mma_nt<T, 8>(e, leaves, w48, out, n, cout, st);
+    if (cout % 256 == 0) return launch_stem_mma_nt<T, 32>(e, leaves, w48, out, n, cout, st, pl);
+    if (cout % 128 == 0) return launch_stem_mma_nt<T, 16>(e, leaves, w48, out, n, cout, st, pl);
+    return launch_stem_mma_nt<T, 8>(e, leaves, w48, out, n, cout, st, pl);
 }
 
 extern "C" {
@@ -409,6 +410,17 @@ int dbaz_nn_stem_mma(dbaz_engine* e, const dbaz_state* leaf_states, const void* 
     if (dtype == DBAZ_BF16) return launch_stem_mma<__nv_bfloat16>(e, leaf_states, (const __nv_bfloat16*)w48, (__nv_bfloat16*)out, n, cout, S(stream));
     if (dtype == DBAZ_F16) return launch_stem_mma<__half>(e, leaf_states, (const __half*)w48, (__half*)out, n, cout, S(stream));
     return fail(e, "dbaz_nn_stem_mma: 16-bit types only");
+}
+
+int dbaz_nn_stem_mma_tiles(dbaz_engine* e, const dbaz_state* leaf_states, const void* w48, void* tiles, int64_t n, uint64_t stream) {
+    if (!e || !leaf_states || !w48 || !tiles) return 1;
+    if (n <= 0) return 0;
+    const TowerGeom g = tower_geom(e->board.rows, e->board.cols);
+    if (!g.ok) return fail(e, "dbaz_nn_stem_mma_tiles: the tower kernel does not support this board");
+    if (n * e->board.rows * e->board.cols >= ((int64_t)1 << 31)) return fail(e, "dbaz_nn_stem_mma_tiles: too many rows");
+    DeviceGuard guard(e->cfg.device);
+    return launch_stem_mma<__nv_bfloat16>(e, leaf_states, (const __nv_bfloat16*)w48, (__nv_bfloat16*)tiles, n, TOWER_C, S(stream),
+                                          StemPlanar{g.nb, g.WP, g.plane, g.buf});
 }
 
 int dbaz_nn_heads(dbaz_engine* e, const void* logits, int32_t ld, int32_t dtype, float* priors, float* values, int64_t n,

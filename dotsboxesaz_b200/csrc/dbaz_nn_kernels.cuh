@@ -370,10 +370,13 @@ __global__ void k_nn_stem_mma_pack(const uint16_t* __restrict__ w48, uint2* __re
     packed[i] = v;
 }
 
+// nb != 0: write the output as planar tiles of the residual-tower kernel instead of NHWC
+struct StemPlanar { int nb, wp, plane, buf; };
+
 template <typename T, int NT>
 __global__ void __launch_bounds__(STEM_WARPS * 32)
 k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /*fragment order, k_nn_stem_mma_pack*/, T* __restrict__ out,
-              int n, int cout, int H, int W) {
+              int n, int cout, int H, int W, StemPlanar pl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NC = 8 * NT;                       // channels per work item
     constexpr int PARTS = NT >= 16 ? 2 : 1;          // the tile leaves through the stage in PARTS column parts
@@ -482,11 +485,29 @@ k_nn_stem_mma(const dbaz_state* __restrict__ leaves, const T* __restrict__ w48 /
             __syncwarp();
             constexpr int CH_PER_ROW = NCP * 2 / 16;  // 16-byte pieces per row segment
 #pragma unroll 4
-            for (int q = lane; q < 16 * CH_PER_ROW; q += 32) {
-                const int rr = q / CH_PER_ROW, cc = q % CH_PER_ROW;
-                if ((uint32_t)rr < rows_here) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)rr * STAGE_ROW + cc * 16);
-                    *reinterpret_cast<uint4*>(obase + (size_t)rr * cout * 2 + (size_t)part * NCP * 2 + cc * 16) = v;
+            if (pl.nb == 0) {
+                for (int q = lane; q < 16 * CH_PER_ROW; q += 32) {
+                    const int rr = q / CH_PER_ROW, cc = q % CH_PER_ROW;
+                    if ((uint32_t)rr < rows_here) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)rr * STAGE_ROW + cc * 16);
+                        *reinterpret_cast<uint4*>(obase + (size_t)rr * cout * 2 + (size_t)part * NCP * 2 + cc * 16) = v;
+                    }
+                }
+            } else {
+                // planar tiles of the residual-tower kernel (include/dbaz_b200.h: dbaz_nn_tower): consecutive rows of one
+                // channel group are consecutive 16-byte slots, so lanes run over the rows
+                for (int q = lane; q < 16 * CH_PER_ROW; q += 32) {
+                    const int cc = q >> 4, rr = q & 15;
+                    if ((uint32_t)rr < rows_here) {
+                        const uint32_t row = r0 + (uint32_t)rr;
+                        const uint32_t leaf = row / (uint32_t)HW, pos = row - leaf * (uint32_t)HW;
+                        const uint32_t hh = pos / (uint32_t)W, ww = pos - hh * (uint32_t)W;
+                        const uint32_t tile = leaf / (uint32_t)pl.nb, j = (leaf - tile * (uint32_t)pl.nb) * (uint32_t)pl.wp + ww;
+                        const uint32_t cg = (uint32_t)(chunk * NC + part * NCP) / 8u + (uint32_t)cc;
+                        const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)rr * STAGE_ROW + cc * 16);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(out) + (size_t)tile * (size_t)pl.buf + 128 + (size_t)cg * (size_t)pl.plane +
+                                                  (size_t)(hh * 128u + j) * 16) = v;
+                    }
                 }
             }
         }

@@ -150,6 +150,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// {bf16(max(hi, 0)), bf16(max(lo, 0))}: the ReLU rides in the conversion
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
@@ -401,19 +407,24 @@ k_resnet_tower(const __grid_constant__ CUtensorMap wmap, const TowerParams P) {
                                              : "r"(dst + cell + (uint32_t)c * (uint32_t)PLANE));
                         }
                         tmem_ld_wait();
+                        // bias (+ residual) in fp32, ReLU inside the conversion to bf16x2; rows that hold no board point
+                        // (pad column, guard rows) are written as zeros: they are the zero padding of the next convolution
                         uint32_t o[16];
+                        if (row_ok) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const uint32_t rr[4] = {res[c].x, res[c].y, res[c].z, res[c].w};
+                            for (int c = 0; c < 4; ++c) {
+                                const uint32_t rr[4] = {res[c].x, res[c].y, res[c].z, res[c].w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int i = 8 * c + 2 * e;
-                                float v0 = __uint_as_float(r[i]) + b[i], v1 = __uint_as_float(r[i + 1]) + b[i + 1];
-                                if (residual) { v0 += bf16_lo(rr[e]); v1 += bf16_hi(rr[e]); }
-                                v0 = row_ok ? fmaxf(v0, 0.0f) : 0.0f;
-                                v1 = row_ok ? fmaxf(v1, 0.0f) : 0.0f;
-                                o[4 * c + e] = pack_bf16(v0, v1);
+                                for (int e = 0; e < 4; ++e) {
+                                    const int i = 8 * c + 2 * e;
+                                    float v0 = __uint_as_float(r[i]) + b[i], v1 = __uint_as_float(r[i + 1]) + b[i + 1];
+                                    if (residual) { v0 += bf16_lo(rr[e]); v1 += bf16_hi(rr[e]); }
+                                    o[4 * c + e] = pack_relu_bf16(v0, v1);
+                                }
                             }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = 0u;
                         }
                         if (!last) {
 #pragma unroll

@@ -319,6 +319,11 @@ class Engine:
         n_tiles = -(-int(n) // g["nb"])
         return torch.zeros((n_tiles, g["tile_bytes"]), dtype=torch.uint8, device=self.device)
 
+    def nn_stem_mma_tiles(self, leaf_states, packed, tiles):
+        """nn_stem_mma() with 64 bf16 output channels written straight into the tower's planar tiles."""
+        self._ck(self.lib.dbaz_nn_stem_mma_tiles(self._h, _ptr(leaf_states), _ptr(packed), _ptr(tiles), leaf_states.shape[0], self._stream()))
+        return tiles
+
     def tower_planarize(self, nhwc, tiles):
         """[n, L+1, C+1, 64] bf16 (contiguous NHWC) -> planar tiles, in place on `tiles`."""
         n = nhwc.shape[0]

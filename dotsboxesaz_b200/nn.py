@@ -10,6 +10,7 @@ exp(log p) and v into the engine's float32 buffers -- all on the current stream,
 host round trip, so Engine.run_search can capture whole waves in a CUDA graph.
 """
 import asyncio
+import copy
 import logging
 import os
 
@@ -189,8 +190,21 @@ class NeuralNetWrapper:
         import torch.utils.data as data
         writer = writer or _NullWriter()
         tp = self.params.nn.train_params
-        train_data = data.DataLoader(train_dataset, tp.train_batch_size, shuffle=True, drop_last=True)
-        val_data = data.DataLoader(val_dataset, tp.val_batch_size, shuffle=False, drop_last=True) if val_dataset is not None else None
+        # datasets that live on the device (samples.DeviceDataset) hand out shuffled device batches themselves; anything
+        # else goes through a DataLoader as in the reference (nn.py:177-181)
+        class _Batches:
+            def __init__(self, ds, bs, shuffle):
+                self.ds, self.bs, self.shuffle = ds, bs, shuffle
+
+            def __iter__(self):
+                return self.ds.batches(self.bs, shuffle=self.shuffle, drop_last=True)
+
+        def loader(ds, bs, shuffle):
+            if hasattr(ds, "batches"):
+                return _Batches(ds, bs, shuffle)
+            return data.DataLoader(ds, bs, shuffle=shuffle, drop_last=True)
+        train_data = loader(train_dataset, tp.train_batch_size, True)
+        val_data = loader(val_dataset, tp.val_batch_size, False) if val_dataset is not None else None
         criterion = AlphaZeroLoss()
         optimizer = torch.optim.SGD(self.model.parameters(), lr=tp.lr, **tp.optimizer_params)
         batch_i = 0
@@ -294,7 +308,7 @@ class DeviceEvaluator:
     def __init__(self, model, engine, dtype=torch.bfloat16, channels_last=True):
         self.engine = engine
         self.dtype = dtype
-        self.model = model.to(engine.device).train(False)
+        self.model = copy.deepcopy(model).to(engine.device).train(False)  # never move, retype or freeze the caller's (training) module
         if dtype != torch.float32:
             self.model = self.model.to(dtype)
         if channels_last:
@@ -419,7 +433,41 @@ def tower_reference(x_nhwc, w3, b3, w_head=None, b_head=None):
     return out.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
 
 
-class FusedSimpleNN:
+def _copy_plan_tensors(dst, src, path="plan"):
+    """dst <- src for every tensor reachable through tuples / lists / dicts of the two plans, IN PLACE (same addresses:
+    CUDA graphs captured around the plan stay valid).  Structures must match; None on the src side (buffers a
+    weights-only plan did not allocate) is skipped."""
+    if src is None:
+        return
+    if isinstance(dst, torch.Tensor):
+        if not isinstance(src, torch.Tensor) or dst.shape != src.shape or dst.dtype != src.dtype:
+            raise RuntimeError("plan reload: %s changed shape or type" % path)
+        dst.copy_(src)
+    elif isinstance(dst, (tuple, list)):
+        if not isinstance(src, (tuple, list)) or len(dst) != len(src):
+            raise RuntimeError("plan reload: %s changed structure" % path)
+        for i, (d, s_) in enumerate(zip(dst, src)):
+            _copy_plan_tensors(d, s_, "%s[%d]" % (path, i))
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_plan_tensors(dst[k], src.get(k), "%s.%s" % (path, k))
+
+
+class _ReloadablePlan:
+    """load(model): fold `model`'s current weights into this plan's tensors in place.  A coach generation changes the
+    weights, not the architecture, so the plan object -- and with it every CUDA graph the engine captured around it
+    (keyed by the evaluator object) -- survives the update; only the folded weights are recomputed."""
+
+    def load(self, model):
+        fresh = type(self)(model, self.engine, dtype=self.dtype, _buffers=False, **self._ctor)
+        for name, val in self.__dict__.items():
+            if name in ("engine", "_ctor") or not isinstance(val, (torch.Tensor, tuple, list, dict)):
+                continue
+            _copy_plan_tensors(val, fresh.__dict__.get(name), name)
+        return self
+
+
+class FusedSimpleNN(_ReloadablePlan):
     """Inference plan for SimpleNN (dots_boxes_nn.py:61-98), 9 kernels per batch instead of the module's ~45.
 
     Every layer is conv/linear -> ReLU -> eval-mode BatchNorm (y = s*r + t).  The affine is pushed into the NEXT
@@ -432,21 +480,22 @@ class FusedSimpleNN:
     policy and value heads are one GEMM.  Same function as the module in eval mode up to rounding of the compute
     dtype (tests/test_gpu_nn.py)."""
 
-    def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True):
+    def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True, _buffers=True):
         self.engine, self.dtype = engine, dtype
+        self._ctor = {"use_stem": use_stem}
         dev = engine.device
-        model = model.to(dev).train(False)
+        model = copy.deepcopy(model).to(dev).train(False)  # never move or retype the caller's (training) module
         rows, cols = engine.rows, engine.cols
         cap = engine.n_games * engine.max_pending
         self.stem = self.stem_mma = None
         c0 = model.conv0
         if use_stem and use_stem != "fma" and _stem_mma_ok(c0, engine, dtype):
             self.stem_mma = engine.nn_stem_mma_pack(_stem_mma_table(c0).to(dtype))      # r0 = relu(conv0(x) + b0), tensor cores
-            self.stem_out = torch.empty((cap, rows, cols, c0.out_channels), dtype=dtype, device=dev)
+            self.stem_out = torch.empty((cap, rows, cols, c0.out_channels), dtype=dtype, device=dev) if _buffers else None
         elif use_stem and dtype in (torch.bfloat16, torch.float16) and (rows, cols) in ((4, 4), (6, 6), (3, 3), (5, 5)):
             ones = torch.ones(c0.out_channels, device=dev)
             self.stem = _stem_tables(c0, rows, cols) + (ones, torch.zeros_like(ones))  # the same on the CUDA cores
-            self.stem_out = torch.empty((cap, rows, cols, c0.out_channels), dtype=dtype, device=dev)
+            self.stem_out = torch.empty((cap, rows, cols, c0.out_channels), dtype=dtype, device=dev) if _buffers else None
         else:
             self.conv0 = (_cl(c0.weight.detach(), dtype), c0.bias.detach().to(dtype), tuple(c0.padding))
         self.convs = []
@@ -513,17 +562,18 @@ def N_CH_OUT(model):
     return model.conv4.out_channels
 
 
-class FusedResNetZero:
+class FusedResNetZero(_ReloadablePlan):
     """Inference plan for ResNetZero (nn.py:108-122).  Here BatchNorm sits between conv and ReLU, so it folds into
     the conv's own weights (per output channel) and bias, and every conv of the tower is ONE cuDNN kernel with its
     epilogue fused: conv-bias-ReLU for conv1 of a block, conv-add-bias-ReLU (z = the block input) for conv2 -- two
     kernels per residual block.  The input BatchNorm folds into the stem tables (leaf gather + conv0 + ReLU from the
     packed leaf states, own kernel); both 1x1 head convs are one conv, both head FCs one GEMM."""
 
-    def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True, use_tower=True):
+    def __init__(self, model, engine, dtype=torch.bfloat16, use_stem=True, use_tower=True, _buffers=True):
         self.engine, self.dtype = engine, dtype
+        self._ctor = {"use_stem": use_stem, "use_tower": use_tower}
         dev = engine.device
-        model = model.to(dev).train(False)
+        model = copy.deepcopy(model).to(dev).train(False)  # never move or retype the caller's (training) module
         cap = engine.n_games * engine.max_pending
 
         def conv_fold(conv, bn):
@@ -543,11 +593,11 @@ class FusedResNetZero:
         if use_stem and use_stem != "fma" and _stem_mma_ok(c0, engine, dtype):
             s0_, t0_ = _bn_affine(model.resnet.bn0)
             self.stem_mma = engine.nn_stem_mma_pack(_stem_mma_table(c0, s_in, t_in, s0_, t0_).to(dtype))  # relu(bn0(conv0(bn_input(x))))
-            self.stem_out = torch.empty((cap, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
+            self.stem_out = torch.empty((cap, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev) if _buffers else None
         elif (use_stem and dtype in (torch.bfloat16, torch.float16) and not isinstance(c0, nn.Sequential) and tuple(c0.padding) == (1, 1)
                 and c0.out_channels in (8, 16, 32, 64, 128, 256) and (engine.rows, engine.cols) in ((4, 4), (6, 6), (3, 3), (5, 5))):
             self.fused_stem = _stem_tables(c0, engine.rows, engine.cols, s_in, t_in) + _bn_affine(model.resnet.bn0)
-            self.stem_out = torch.empty((cap, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
+            self.stem_out = torch.empty((cap, engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev) if _buffers else None
         else:
             self.in_scale = s_in.view(1, -1, 1, 1).to(dtype)
             self.in_shift = t_in.view(1, -1, 1, 1).to(dtype)
@@ -579,8 +629,8 @@ class FusedResNetZero:
             self.tower = (packed, bias, w3.shape[0], cp + cv)
             # one wave of the tower's persistent grid: the adaptive wave loop puts its batch sizes at multiples of it
             self.batch_quantum = engine.tower_geometry()["nb"] * engine.n_sms
-            self.tower_tiles = engine.tower_tiles(cap)
-            self.tower_out = torch.empty((cap, engine.rows, engine.cols, cp + cv), dtype=dtype, device=dev)
+            self.tower_tiles = engine.tower_tiles(cap) if _buffers else None
+            self.tower_out = torch.empty((cap, engine.rows, engine.cols, cp + cv), dtype=dtype, device=dev) if _buffers else None
         hw = engine.rows * engine.cols
         A, fi = engine.A, vh.fc0.out_features
         # one GEMM over the NHWC-flattened [hw, cp+cv] head activations: columns [0, A) policy logits, [A, A+fi) value hidden
@@ -593,13 +643,21 @@ class FusedResNetZero:
         self.v_b = vh.fc1.bias.detach().to(dtype)
         self.A = A
         self.ld = (A + 1 + 7) // 8 * 8
-        self.logits = torch.zeros((cap, self.ld), dtype=dtype, device=dev)
-        self.engine_launches = (2 if (self.fused_stem is not None or self.stem_mma is not None) else 1) + (2 if self.tower is not None else 0)  # own kernels per batch
+        self.logits = torch.zeros((cap, self.ld), dtype=dtype, device=dev) if _buffers else None
+        self.engine_launches = (2 if (self.fused_stem is not None or self.stem_mma is not None) else 1) + (1 if self.tower is not None else 0)  # own kernels per batch: (stem,) (tower,) heads
+        if self.tower is not None:
+            self.stem_out = None  # the stem writes the tower's tiles
         engine.set_planes(dtype, channels_last=True)
 
     @torch.no_grad()
     def __call__(self, eng):
         n = eng.n_rows
+        if self.tower is not None:
+            # stem -> tower -> heads: the stem writes the tower's planar tiles, no NHWC activation tensor in between
+            packed, bias, n_stages, hc = self.tower
+            eng.nn_stem_mma_tiles(eng.leaf_states, self.stem_mma, self.tower_tiles)
+            h = eng.tower(self.tower_tiles, packed, bias, n_stages, hc, self.tower_out[:n]).reshape(n, -1)
+            return self._heads(eng, h, n)
         if self.stem_mma is not None:
             x = eng.nn_stem_mma(eng.leaf_states, self.stem_mma, self.stem_out[:n]).permute(0, 3, 1, 2)
         elif self.fused_stem is not None:
@@ -608,15 +666,13 @@ class FusedResNetZero:
         else:
             w, b, pad = self.stem
             x = _conv_relu(eng.planes * self.in_scale + self.in_shift, w, b, pad)
-        if self.tower is not None:
-            packed, bias, n_stages, hc = self.tower
-            eng.tower_planarize(self.stem_out[:n], self.tower_tiles)
-            h = eng.tower(self.tower_tiles, packed, bias, n_stages, hc, self.tower_out[:n]).reshape(n, -1)
-        else:
-            for (w1, b1, p1), (w2, b2, p2) in self.blocks:
-                x = _conv_add_relu(_conv_relu(x, w1, b1, p1), w2, x, b2, p2)
-            hw_, hb = self.head_conv
-            h = _conv_relu(x, hw_, hb, (0, 0)).permute(0, 2, 3, 1).reshape(n, -1)
+        for (w1, b1, p1), (w2, b2, p2) in self.blocks:
+            x = _conv_add_relu(_conv_relu(x, w1, b1, p1), w2, x, b2, p2)
+        hw_, hb = self.head_conv
+        h = _conv_relu(x, hw_, hb, (0, 0)).permute(0, 2, 3, 1).reshape(n, -1)
+        return self._heads(eng, h, n)
+
+    def _heads(self, eng, h, n):
         out = torch.addmm(self.head_b, h, self.head_w)
         logits = self.logits[:n]
         logits[:, :self.A] = out[:, :self.A]

@@ -13,6 +13,7 @@ generate_games   self_play.py:291-306 re-targeted: games are sharded by index ov
 """
 import logging
 import math
+import time
 
 import ctypes as C
 
@@ -571,9 +572,17 @@ def compute_elo(elo_params, params, generations, elos, models=None, engine=None)
     for p in params:
         p.self_play.merge(elo_params.self_play_override)
     n = int(elo_params.n_games)
+    own_engine = engine is None
     if engine is None:
         engine = _engine.Engine(tuple(params[0].game.clazz.BOARD_DIM), n_games=n,
                                 max_nodes=int(params[0].self_play.get("max_nodes_per_tree", 8192) or 8192))
+    # The eval cache is keyed by the position alone: with two nets in play it would serve each player the other
+    # generation's evaluations (the reference switches its LRU off for model comparison, self_play.py:230).  A caller's
+    # engine gets its table back afterwards.  DualEvaluator also assumes row == slot * n_games + tree: no compact rows.
+    saved_cache = engine.eval_cache_log2
+    if saved_cache:
+        engine.set_eval_cache(0)
+    engine.set_mode(False, engine.max_inline)
     if models is None:
         models = []
         for p, g in zip(params, generations):
@@ -627,6 +636,10 @@ def compute_elo(elo_params, params, generations, elos, models=None, engine=None)
     elo0, elo1 = elo_rating2(elos[0], elos[1], n0, n1, K=30)
     print(f"generation {generations[0]}: wins={n0}, elo={elos[0]} -> {elo0}")
     print(f"generation {generations[1]}: wins={n1}, elo={elos[1]} -> {elo1}")
+    if own_engine:
+        engine.close()
+    elif saved_cache:
+        engine.set_eval_cache(saved_cache)
     return elo0, elo1, n1 / max(1, n0 + n1)
 
 
@@ -683,45 +696,106 @@ def default_eval_cache(params):
     return max(16, int(np.log2((8 << 30) / (16 * A))))
 
 
-def generate_games(hdf_file_name, generation, nn_class, n_games, params, n_workers=None, games_per_workers=10,
-                   engine=None, evaluator=None, writer=None):
-    """self_play.py:291-306.  One process per GPU (torch.distributed), `n_games` sharded by index; each rank
-    plays its shard in lock-step batches of engine.n_games.  Rank 0 receives all sample rows and hands them
-    to `writer(hdf_file_name, "fresh", df)` (default: pandas HDFStore append, as utils/utils.py:94-96)."""
-    import torch.distributed as dist
+def shard_engine(params, n_shard_games, device=None):
+    """One engine per rank, sized for THIS rank's shard of a generation (never for the global game count) and meant to
+    live for the whole coach run: its node pool and eval cache are raw device memory that only engine.close() returns."""
     from . import engine as _engine
+    cap = int(params.self_play.get("concurrent_games", 4096) or 4096)
+    n_chunks = max(1, -(-int(n_shard_games) // cap))
+    slots = max(1, -(-int(n_shard_games) // n_chunks))  # equal chunks: the last one is short by less than n_chunks games
+    return _engine.Engine(tuple(params.game.clazz.BOARD_DIM), n_games=slots,
+                          max_nodes=int(params.self_play.get("max_nodes_per_tree", 8192) or 8192),
+                          eval_cache=default_eval_cache(params), device=device)
+
+
+def game_seed(base_seed, generation, game_idx):
+    """Seed of one game's legacy-MT19937 stream: a function of (base seed, generation, game index), so that no two
+    generations replay the same noise and move-sampling uniforms (the reference's workers never reseed either)."""
+    return int(np.random.SeedSequence([int(base_seed), int(generation), int(game_idx)]).generate_state(1)[0])
+
+
+def play_shard(params, generation, engine, evaluator, indices, want_frames=False):
+    """This rank's games of one generation.  Returns (samples.SampleBatch on the engine's device, [DataFrame, ...] if
+    want_frames, info dict).  Full-width batches run every game at its own pace (play_games_async: device RNG, samples stay
+    in HBM); `params.self_play.rng == "host"` keeps one legacy NumPy stream per game (reference-exact games, host loop).
+    A short last chunk is padded with throw-away games (index -1) so that it takes the same device-resident path."""
+    from . import samples
+    indices = list(indices)
+    base_seed = int(params.self_play.get("seed", 0) or 0)
+    host_rng = params.self_play.get("rng", "device") == "host"
+    n = engine.n_games
+    batches, frames = [], []
+    info = {"sims": 0, "games": len(indices), "chunks": 0}
+    for lo in range(0, len(indices), n):
+        chunk = indices[lo:lo + n]
+        sp = BatchedSelfPlay(engine, evaluator, params)
+        if host_rng:
+            sp.play_games(chunk, seeds=[game_seed(base_seed, generation, i) for i in chunk])
+            df = sp.get_datasets(generation, True)
+            batches.append(samples.batch_from_frame(df, engine.device, generation))
+        else:
+            padded = chunk + [-1] * (n - len(chunk))
+            seed = game_seed(base_seed, generation, chunk[0])
+            (sp.play_games_async if (sp.adaptive and sp.pending == 1 and sp.graph_waves > 0) else sp.play_games_device)(padded, seed=seed)
+            batches.append(samples.batch_from_selfplay(sp, generation))
+            df = None
+            if want_frames:
+                df = sp.get_datasets(generation, True)
+                df = df[df.index.get_level_values("game_idx") >= 0]
+        if want_frames:
+            frames.append(df)
+        info["sims"] += sp.total_sims
+        info["chunks"] += 1
+    return samples.SampleBatch.cat(batches), frames, info
+
+
+def generate_games(hdf_file_name, generation, nn_class, n_games, params, n_workers=None, games_per_workers=10,
+                   engine=None, evaluator=None, writer=None, return_batch=False):
+    """self_play.py:291-306.  One process per GPU (torch.distributed), `n_games` sharded by index; every rank plays its
+    shard on its own engine (play_shard), the (features, pi, z) rows are gathered to rank 0 as device tensors with one
+    NCCL collective (samples.gather_batches -- the reference's locked HDF append, self_play.py:264-265), and the
+    DataFrame of self_play.py:95-156 is only built for export: each rank hands its own rows to
+    `writer(hdf_file_name, "fresh", df)` (default: a part of the replay store) unless
+    `params.self_play.export_frames` is False.  Returns the DataFrame of this rank's rows (None without export), or
+    with return_batch the tuple (df, gathered SampleBatch on rank 0 / None elsewhere, info)."""
+    import torch.distributed as dist
+    from . import samples
     from .nn import make_evaluator
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     mine = shard_game_indices(n_games, rank, world)
-    if engine is None:
-        slots = max(1, min(len(mine), int(params.self_play.get("concurrent_games", 4096) or 4096)))
-        engine = _engine.Engine(tuple(params.game.clazz.BOARD_DIM), n_games=slots,
-                                max_nodes=int(params.self_play.get("max_nodes_per_tree", 8192) or 8192),
-                                eval_cache=default_eval_cache(params))
-    engine.clear_eval_cache()  # cached evaluations belong to the previous generation's weights
-    if evaluator is None:
-        model = nn_class(params)
-        if generation != 0:
-            model.load_parameters(generation - 1, to_device=engine.device)
-        broadcast_model(model.to(engine.device))
-        evaluator = make_evaluator(model, engine)
-    frames = []
-    base_seed = int(params.self_play.get("seed", 0) or 0)
-    host_rng = params.self_play.get("rng", "device") == "host"  # "host": one legacy NumPy stream per game (reference-exact games)
-    for lo in range(0, len(mine), engine.n_games):
-        chunk = mine[lo:lo + engine.n_games]
-        sp = BatchedSelfPlay(engine, evaluator, params)
-        if host_rng or len(chunk) < engine.n_games:
-            sp.play_games(chunk, seeds=[base_seed + i for i in chunk])
-        else:
-            sp.play_games_device(chunk, seed=base_seed + 7919 * generation + chunk[0])
-        frames.append(sp.get_datasets(generation, True))
-    df = pd.concat(frames) if frames else None
-    df = gather_samples(df)
-    if rank == 0 and df is not None:
-        df["training"] = np.zeros(len(df.index), dtype=np.int8)
-        if writer is None:
-            from .utils.utils import write_to_hdf as writer
-        writer(hdf_file_name, "fresh", df)
-    return df
+    own_engine = engine is None
+    if own_engine:
+        engine = shard_engine(params, len(mine))
+    try:
+        engine.clear_eval_cache()  # cached evaluations belong to the previous generation's weights
+        if evaluator is None:
+            model = nn_class(params)
+            if generation != 0:
+                model.load_parameters(generation - 1, to_device=engine.device)
+            broadcast_model(model.to(engine.device))
+            evaluator = make_evaluator(model, engine)
+        export = bool(params.self_play.get("export_frames", True))
+        t0 = time.time()
+        batch, frames, info = play_shard(params, generation, engine, evaluator, mine, want_frames=export)
+        torch.cuda.synchronize(engine.device)
+        info["play_s"] = time.time() - t0
+        t0 = time.time()
+        gathered = samples.gather_batches(batch, engine.F, engine.A, dst=0, device=engine.device)
+        torch.cuda.synchronize(engine.device)
+        info["gather_s"] = time.time() - t0
+        df = None
+        if export and frames:
+            t0 = time.time()
+            df = pd.concat(frames)
+            df["training"] = np.zeros(len(df.index), dtype=np.int8)
+            if writer is None:
+                from .utils.utils import ReplayStore
+                store = ReplayStore(hdf_file_name)
+                writer = lambda f, k, d: store.append(k, d, part="r%03d" % rank)
+            writer(hdf_file_name, "fresh", df)
+            info["export_s"] = time.time() - t0
+    finally:
+        if own_engine:
+            engine.close()
+    return (df, gathered, info) if return_batch else df

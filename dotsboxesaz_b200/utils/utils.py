@@ -89,14 +89,18 @@ class ReplayStore:
         os.makedirs(d, exist_ok=True)
         return d
 
-    def append(self, key, df):
+    def append(self, key, df, part=None):
+        """part: a writer-specific tag (e.g. the rank) so that several processes can append to the same table without
+        agreeing on a part number; parts are read back in name order."""
         import os
+        import time
         import pandas as pd
         if self.hdf:
             return write_to_hdf(self.path, key, df)
         d = self._part_dir(key)
         n = len([f for f in os.listdir(d) if f.endswith(".parquet")])
-        df.reset_index().to_parquet(os.path.join(d, "part%05d.parquet" % n))
+        name = "part%05d.parquet" % n if part is None else "part%016d_%s.parquet" % (time.time_ns() // 1000, part)
+        df.reset_index().to_parquet(os.path.join(d, name))
 
     def has(self, key):
         import os

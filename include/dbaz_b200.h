@@ -231,6 +231,9 @@ int dbaz_nn_heads(dbaz_engine *e, const void *logits, int32_t ld, int32_t dtype,
  * out: [n][L+1][C+1][head_cout ? head_cout : 64] bf16 = relu(head(tower(x))) resp. tower(x).
  * Stage s odd adds the input of stage s - 1 (the residual) before the ReLU.  head_cout in {0, 16, 32}. */
 int dbaz_nn_tower_geometry(dbaz_engine *e, int32_t *out8);
+/* dbaz_nn_stem_mma() (64 output channels, bf16) writing planar tiles directly: stem -> tower without an NHWC pass. */
+int dbaz_nn_stem_mma_tiles(dbaz_engine *e, const dbaz_state *leaf_states, const void *w48, void *tiles, int64_t n,
+                           uint64_t stream);
 int dbaz_nn_tower_planarize(dbaz_engine *e, const void *nhwc, void *tiles, int64_t n, uint64_t stream);
 int dbaz_nn_tower(dbaz_engine *e, const void *tiles, const void *packed_w, const float *bias, int32_t n_stages,
                   int32_t head_cout, void *out, int64_t n, uint64_t stream);

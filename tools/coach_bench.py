@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--sims", type=int, default=200)
     ap.add_argument("--generations", type=int, default=2)
     ap.add_argument("--blocks", type=int, default=20)
+    ap.add_argument("--export", action="store_true", help="also write every rank's rows to the replay store (DataFrame + parquet)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -52,7 +53,8 @@ def main():
     params.nn.train_params.train_batch_size = 1024
     params.nn.train_params.val_batch_size = 1024
     t0 = time.time()
-    timings = coach.learn_to_play(params, 0, args.generations)
+    params.self_play.export_frames = bool(args.export)
+    timings = coach.learn_to_play(params, 0, args.generations - 1)  # to_generation is inclusive (coach.py:143)
     if rank == 0:
         for t in timings:
             t.update(board=args.board, net=args.net, games=args.games, sims_per_move=args.sims, n_gpus=world)
