@@ -151,3 +151,112 @@ def test_reference_selfplay_fixture_at_800_sims():
             assert np.array_equal(df.to_numpy(dtype=np.float64), np.array(G["rows"], dtype=np.float64))
         finally:
             eng.close()
+
+
+class _LoggingEvaluator:
+    """Wraps a real evaluator and remembers every (leaf state -> priors, value) it produced, so that the oracle can be
+    given IDENTICAL net outputs (north_star: visit counts bit-exact given identical NN outputs)."""
+
+    def __init__(self, ev, engine):
+        self.ev, self.eng, self.log = ev, engine, []
+        self.engine_launches = getattr(ev, "engine_launches", 0)
+
+    def __call__(self, eng):
+        self.ev(eng)
+        self.log.append((eng.leaf_kind.clone(), eng.leaf_states.clone(), eng.priors.clone(), eng.values.clone()))
+
+    def table(self):
+        out = {}
+        for kind, st, p, v in self.log:
+            rows = torch.nonzero(kind > 0).reshape(-1)
+            s = st[rows].cpu().numpy().view(np.uint8).reshape(-1, 32)
+            pn, vn = p[rows].cpu().numpy(), v[rows].cpu().numpy()
+            for i in range(len(rows)):
+                out[bytes(s[i, :22])] = (pn[i].copy(), np.float32(vn[i]))   # edges, btc2, to_play, just_played
+        return out
+
+
+def test_config3_5x5_800sims_resnet20_bf16_vs_oracle():
+    """BASELINE configs[3] at its real depth: 5x5 boxes, 800 simulations per move, ResNetZero with 20 residual blocks in
+    bf16 through the tcgen05 tower kernel.  Every evaluation the net produced is logged; oracle trees fed the same
+    outputs must end with identical visit counts, W and tree statistics."""
+    from dotsboxesaz_b200 import engine
+    from dotsboxesaz_b200.nn import FusedResNetZero, ResNetZero, resnet_zero_parameters
+    from dotsboxesaz_b200.utils.utils import DotDict
+    from oracle import oracle
+    n, sims = 96, 800
+    eng = engine.Engine((5, 5), n_games=n, max_nodes=sims + 8)
+    try:
+        torch.manual_seed(0)
+        model = ResNetZero(DotDict({"nn": {"model_parameters": resnet_zero_parameters((5, 5), nb_blocks=20)}}))
+        plan = FusedResNetZero(model, eng, dtype=torch.bfloat16)
+        assert plan.tower is not None and plan.tower[2] == 40
+        ev = _LoggingEvaluator(plan, eng)
+        # roots: a few random plies each, built with the engine's own rules
+        g = torch.Generator(device=eng.device).manual_seed(7)
+        st = eng.new_states(n)
+        for ply in range(10):
+            legal = eng.valid_moves(st).float()
+            mv = torch.multinomial(legal + 1e-9, 1, generator=g).reshape(-1).int()
+            eng.play(st, torch.where(torch.arange(n, device=eng.device) % 11 > ply, mv, torch.full_like(mv, -1)))
+        rs = np.random.RandomState(5)
+        valid = eng.valid_moves(st).cpu().numpy()
+        noise = rs.dirichlet(np.ones(eng.A) * NOISE[0], size=n) * valid
+        eng.reset_roots(st)
+        eng.run_search(sims, ev, noise=torch.from_numpy(noise), coeff=NOISE[1])   # plain wave loop: every leaf goes to the net, row == tree
+        vis = eng.root_visits().cpu().numpy()
+        W, P, S, U = (x.cpu().numpy() for x in eng.root_children())
+        stats, rootW, q = (x.cpu().numpy() for x in eng.tree_stats())
+        assert eng.status()["errors"] == 0
+        table = ev.table()
+        assert len(table) > 20000
+        states_np = eng.states_to_numpy(st)
+        misses = [0]
+        checked = 0
+        for t in range(0, n, 12):
+            # the oracle tree of root t with a net that answers from the log
+            root = oracle.OracleGame(5, 5)
+
+            def lookup(og):
+                b = og.board().ravel()
+                e = [0, 0]
+                for a in np.flatnonzero(b == 255):
+                    e[int(a) >> 6] |= 1 << (int(a) & 63)
+                key = np.zeros(22, dtype=np.uint8)
+                key[:16] = np.frombuffer(np.array(e, dtype=np.uint64).tobytes(), dtype=np.uint8)
+                key[16:20] = np.frombuffer(np.array([og.s.btc2[0], og.s.btc2[1]], dtype=np.int16).tobytes(), dtype=np.uint8)
+                key[20] = og.s.to_play
+                key[21] = np.uint8(og.s.just_played & 0xff)
+                hit = table.get(bytes(key))
+                if hit is None:
+                    misses[0] += 1
+                    return np.full(eng.A, 1.0 / eng.A, np.float32), np.zeros(1, np.float32)
+                return hit[0], np.array([hit[1]], dtype=np.float32)
+            og = _reach(root, states_np[t], eng)
+            tree = oracle.OracleTree(5, 5, og.s, nn=lookup)
+            ov = tree.search(sims, cpuct=CPUCT, noise=noise[t], coeff=NOISE[1])
+            assert misses[0] == 0, "the oracle asked for a position the engine never evaluated"
+            assert np.array_equal(vis[t], ov), ("visit counts", t)
+            r = tree.root()
+            assert np.array_equal(W[t], r["W"]) and np.array_equal(P[t], r["priors"])
+            assert int(stats[t][0]) == r["root_N"] and [int(stats[t][1]), int(stats[t][2]), int(stats[t][3])] == r["stats"][:3]
+            assert np.float32(rootW[t]) == np.float32(r["root_W"])
+            checked += 1
+        assert checked == 8
+    finally:
+        eng.close()
+
+
+def _reach(og, packed, eng):
+    """The oracle game with the engine's packed root state taken as is (the order in which its edges were played is not
+    recoverable, and turn order matters, so the fields are copied rather than replayed)."""
+    og.s.to_play = int(packed["to_play"])
+    og.s.just_played = int(packed["just_played"])
+    og.s.btc2[0], og.s.btc2[1] = int(packed["btc2"][0]), int(packed["btc2"][1])
+    edges = [int(packed["edges"][0]), int(packed["edges"][1])]
+    for a in range(eng.A):
+        if (edges[a >> 6] >> (a & 63)) & 1:
+            og.s.board[a] = 255
+    og.s.hash_lo, og.s.hash_hi = edges[0], edges[1]
+    og.s.hash_btc2 = og.s.btc2[og.s.to_play]
+    return og
