@@ -43,6 +43,7 @@ SYMBOLS = {
     "dbaz_search_reset_roots": (C.c_int, [_P, _P, _U64]),
     "dbaz_search_begin": (C.c_int, [_P, _P, _I32, _P, _D, _U64]),
     "dbaz_search_step": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _U64]),
+    "dbaz_search_step2": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _I32, _I32, _P, _U64]),
     "dbaz_search_stop": (C.c_int, [_P, _U64]),
     "dbaz_search_root_visits": (C.c_int, [_P, _P, _U64]),
     "dbaz_search_root_children": (C.c_int, [_P, _P, _P, _P, _P, _U64]),

@@ -187,7 +187,11 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     ta.stride = 32 + 16 * A;
     ta.max_pending = max_pending;
     e->pending = 1;
-    ta.lut_size = cfg->lut_size > 0 ? cfg->lut_size : 65536;
+    // A node's visit count is bounded by the simulations that can pass through it: with tree reuse at most (moves of a game) x
+    // (simulations per search), and a search cannot run more simulations than the node pool holds.  The default table covers
+    // 128 x (pool size) visits (a 7x7 board has 112 moves), so the device-log fallback of puct_consts() is out of reach.
+    ta.lut_size = cfg->lut_size > 0 ? cfg->lut_size
+                                    : (int)std::max<int64_t>(65536, std::min<int64_t>((int64_t)1 << 23, 128 * ((int64_t)cfg->max_nodes + 1)));
     ta.cpuct = cfg->cpuct;
     ta.cpuct_base = cfg->cpuct_base;
     const size_t arena_bytes = (size_t)ta.n_trees * ta.max_nodes * ta.stride;
@@ -209,7 +213,7 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
               alloc((void**)&ta.lut, (size_t)ta.lut_size * sizeof(double2), "log/sqrt table") &&
               alloc((void**)&ta.act_tab, (size_t)A * 2 * sizeof(uint4), "action table") &&
               alloc((void**)&ta.pend, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4), "pending leaves") &&
-              alloc((void**)&ta.ctr, 8 * sizeof(int), "wave counters") &&
+              alloc((void**)&ta.ctr, 16 * sizeof(int), "wave counters") &&
               alloc((void**)&e->d_status, 8 * sizeof(unsigned long long), "status");
     if (!ok) { dbaz_engine_destroy(e); return 1; }
     if (upload_lut(e)) { g_create_err = e->err; dbaz_engine_destroy(e); return 1; }
@@ -223,9 +227,10 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
     }
     k_build_act_tab<<<1, DBAZ_MAX_ACTIONS>>>(b, const_cast<uint4*>(ta.act_tab));
     cudaMemset(ta.pend, 0, (size_t)max_pending * ta.n_trees * 3 * sizeof(uint4));
-    cudaMemset(ta.ctr, 0, 8 * sizeof(int));
+    cudaMemset(ta.ctr, 0, 16 * sizeof(int));
     cudaMemset(ta.path_wn, 0, (size_t)ta.n_trees * PATH_CAP * sizeof(uint2));
     ta.batch_rows = 0x7fffffff;
+    ta.phase = 0; ta.buf = 0;
     ta.cache_vcell = C;  // action C = horizontal edge (row 0, column C): always a padding cell
     cudaMemset(ta.path, 0, (size_t)max_pending * ta.n_trees * PATH_CAP * sizeof(uint32_t));
     // an all-empty-board root set so that the engine is usable right after create
@@ -513,6 +518,23 @@ int dbaz_search_step(dbaz_engine* e, const float* priors, const float* values, v
         DBAZ_DISPATCH(e, (k_search_step<APL, NW, false><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(
                              e->board, e->ta, e->pending, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, leaf_kind)));
     return launch_ok(e, "k_search_step");
+}
+
+int dbaz_search_step2(dbaz_engine* e, int32_t phase, int32_t buf, int32_t max_inline, const float* priors, const float* values, void* planes,
+                      int32_t dtype, int32_t layout, dbaz_state* leaf_states, uint64_t stream) {
+    if (!e || !planes || !leaf_states) return 1;
+    if (phase != 1 && phase != 2) return fail(e, "dbaz_search_step2: phase must be 1 (absorb) or 2 (chain)");
+    if (phase == 1 && (!priors || !values)) return 1;
+    if (buf < 0 || buf > 1 || max_inline < 0) return fail(e, "dbaz_search_step2: bad batch index / max_inline");
+    if (e->pending != 1 || !e->ta.compact) return fail(e, "dbaz_search_step2 needs max_pending_evals == 1 and compact rows (dbaz_search_set_mode)");
+    if (dtype < DBAZ_F32 || dtype > DBAZ_I16 || layout < 0 || layout > 1) return fail(e, "bad dtype/layout");
+    DeviceGuard guard(e->cfg.device);
+    TreeArgs ta = e->ta;
+    ta.phase = phase; ta.buf = buf; ta.max_inline = max_inline;
+    const int grid = blocks_for(ta.n_trees, TREE_WARPS);
+    DBAZ_DISPATCH(e, (k_search_step<APL, NW, true><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(
+                         e->board, ta, 1, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, nullptr)));
+    return launch_ok(e, "k_search_step (phase)");
 }
 
 int dbaz_search_stop(dbaz_engine* e, uint64_t stream) {

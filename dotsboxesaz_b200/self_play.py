@@ -396,8 +396,8 @@ class BatchedSelfPlay:
         rows, i = ladder[0], 0
         while True:
             graphs[rows].replay()
-            eng.n_launches += self.graph_waves * per_wave + finish_launches
-            eng.n_waves += self.graph_waves
+            eng._count_replay(graphs[rows])
+            eng.n_launches += finish_launches
             slot = counts[i % 64]
             eng.lib.dbaz_search_wave_counts(eng._h, C.c_void_p(slot.data_ptr()), eng._stream())
             fgraph.replay()

@@ -55,7 +55,7 @@ typedef struct dbaz_config {
     int32_t board_l, board_c; /* BoxesState.BOARD_DIM (dots_boxes_game.py:23) */
     int32_t n_games;       /* concurrent games == trees on this GPU */
     int32_t max_nodes;     /* node-pool capacity per tree (>= sims per move + retained subtree) */
-    int32_t lut_size;      /* entries of the host-libm log table for the PUCT constant; 0 = 65536 */
+    int32_t lut_size;      /* entries of the host-libm log table for the PUCT constant; 0 = max(65536, 128 * (max_nodes + 1)): every reachable visit count */
     int32_t max_pending;   /* largest max_pending_evals (in-flight simulations per tree) a search may ask for; 0 = 1 */
     double cpuct;          /* UCTNode.CPUCT (mcts.py:44) */
     double cpuct_base;     /* UCTNode.CPUCT_BASE (mcts.py:45) */
@@ -129,6 +129,22 @@ int dbaz_search_begin(dbaz_engine *e, const int32_t *num_reads, int32_t pending,
  *   never appear: their simulation is completed inside the step, as in the reference where it never awaits. */
 int dbaz_search_step(dbaz_engine *e, const float *priors, const float *values, void *planes, int32_t dtype,
                      int32_t layout, dbaz_state *leaf_states, int8_t *leaf_kind, uint64_t stream);
+/* The same wave as TWO launches, so that the part of it that needs no evaluator runs UNDER the evaluator
+ * (max_pending_evals == 1, compact rows; two leaf batches 0 / 1 that alternate from wave to wave):
+ *   phase 1 "absorb" (before the evaluator of batch `buf`): trees whose pending leaf sits in batch buf ^ 1 -- evaluated by the
+ *     previous wave, priors / values point at THAT batch -- are backed up and run on as in dbaz_search_step; trees in the
+ *     middle of a chain of evaluator-free simulations (terminal leaves, eval-cache hits) run on too; at most `max_inline`
+ *     such simulations complete per tree; leaves go to batch `buf` (planes / leaf_states point at it) behind the rows
+ *     phase 2 of the previous wave put there; a tree whose leaf already waits in batch `buf` is left alone.  Publishes the
+ *     wave counters (dbaz_search_wave_counts).
+ *   phase 2 "chain" (a second stream, concurrently with the evaluator of batch `buf`): only trees WITHOUT a pending leaf run
+ *     on, up to `max_inline` completions, and their leaves go to batch buf ^ 1 from row 0 (planes / leaf_states point at
+ *     batch buf ^ 1; priors / values are not read).
+ * The order of a tree's simulations is untouched, so every result equals dbaz_search_step's.  A sequence of waves must
+ * start with buf = 0, alternate, and end with a phase 1 that no phase 2 follows (nothing is carried across sequences). */
+int dbaz_search_step2(dbaz_engine *e, int32_t phase, int32_t buf, int32_t max_inline, const float *priors,
+                      const float *values, void *planes, int32_t dtype, int32_t layout, dbaz_state *leaf_states,
+                      uint64_t stream);
 /* UCT_search's wall-clock limit (mcts.py:201-203,232-233): no tree starts another simulation; the
  * next dbaz_search_step() only backs up the leaves already pending. */
 int dbaz_search_stop(dbaz_engine *e, uint64_t stream);
