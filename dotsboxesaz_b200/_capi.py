@@ -49,6 +49,7 @@ SYMBOLS = {
     "dbaz_search_root_children": (C.c_int, [_P, _P, _P, _P, _P, _U64]),
     "dbaz_search_tree_stats": (C.c_int, [_P, _P, _P, _P, _U64]),
     "dbaz_search_root_states": (C.c_int, [_P, _P, _U64]),
+    "dbaz_search_node": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U64]),
     "dbaz_search_tree_busy": (C.c_int, [_P, _P, _U64]),
     "dbaz_search_advance_roots": (C.c_int, [_P, _P, _I32, _U64]),
     "dbaz_search_status": (C.c_int, [_P, _P, _U64]),

@@ -560,6 +560,16 @@ int dbaz_search_root_children(dbaz_engine* e, float* W, double* priors, int32_t*
     return launch_ok(e, "k_root_children");
 }
 
+int dbaz_search_node(dbaz_engine* e, int32_t tree, int32_t node, dbaz_state* state_out, float* W, int32_t* N, double* priors,
+                     int32_t* child, int32_t* sign, double* ucb, int32_t* own8, float* own_W, uint64_t stream) {
+    if (!e || !state_out || !W || !N || !priors || !child || !sign || !ucb || !own8 || !own_W) return 1;
+    if (tree < 0 || tree >= e->ta.n_trees) return fail(e, "dbaz_search_node: no such tree");
+    DeviceGuard guard(e->cfg.device);
+    if (e->nw == 1) k_node_view<1><<<1, 32, 0, S(stream)>>>(e->board, e->ta, tree, node, state_out, W, N, priors, child, sign, ucb, own8, own_W);
+    else k_node_view<2><<<1, 32, 0, S(stream)>>>(e->board, e->ta, tree, node, state_out, W, N, priors, child, sign, ucb, own8, own_W);
+    return launch_ok(e, "k_node_view");
+}
+
 int dbaz_search_tree_stats(dbaz_engine* e, int32_t* stats8, float* root_W, float* q, uint64_t stream) {
     if (!e) return 1;
     DeviceGuard guard(e->cfg.device);

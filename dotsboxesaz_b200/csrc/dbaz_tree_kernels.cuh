@@ -1199,6 +1199,53 @@ __global__ void k_root_children(Board b, TreeArgs ta, float* __restrict__ W, dou
     (void)e;
 }
 
+// Any node of one tree for walks from the host (UCTNode.children / print_mcts_tree, mcts.py:47-65,247-272): the node's
+// state, its per-child arrays, the UCB scores children_ucb_score() would return for it, and its own N / W (which live in
+// its parent's child record, or in the tree record for node 0).  One warp.
+template <int NW>
+__global__ void k_node_view(Board b, TreeArgs ta, int tree, int node, dbaz_state* __restrict__ state_out, float* __restrict__ W,
+                            int32_t* __restrict__ N, double* __restrict__ priors, int32_t* __restrict__ child, int32_t* __restrict__ sign,
+                            double* __restrict__ ucb, int32_t* __restrict__ own8, float* __restrict__ own_W) {
+    const int lane = threadIdx.x & 31;
+    const int A = b.A;
+    TreeRec T = ta.trees[tree];
+    if (node < 0 || node >= T.n_nodes) {
+        if (lane == 0) own8[7] = 1;  // no such node
+        return;
+    }
+    char* np = node_ptr(ta, tree, node);
+    dbaz_state h = load_hdr(np);
+    const bool interior = (h.flags & NF_EXPANDED) && !(h.flags & NF_TERMINAL);
+    const Child* ch = node_children(np);
+    int ownN = T.root_N;
+    float ownW = T.root_W;
+    if (node != 0) {
+        const Child pc = node_children(node_ptr(ta, tree, h.parent))[h.parent_action];
+        ownN = pc.N; ownW = pc.W;
+    }
+    const double2 cs = puct_consts(ta, ownN);
+    for (int a = lane; a < A; a += 32) {
+        Child c; c.W = 0.0f; c.N = 0; c.prior = 0.0f; c.child = 0;
+        if (interior) c = ch[a];
+        const double pr = (node == 0 && (T.flags & TF_PRIOR_SET)) ? ta.root_prior[(int64_t)tree * A + a] : (double)c.prior;
+        int sg = 1;  // child_player_changed defaults to +1 until the child is expanded (mcts.py:61-62,119)
+        if (c.child != 0) {
+            dbaz_state chd = load_hdr(node_ptr(ta, tree, c.child));
+            if (chd.flags & NF_EXPANDED) sg = (chd.to_play == (uint8_t)chd.just_played) ? 1 : -1;
+        }
+        W[a] = c.W; N[a] = c.N; priors[a] = pr; child[a] = c.child; sign[a] = sg;
+        ucb[a] = ucb_score<1, NW>(cs.x, cs.y, c, pr, sg);
+    }
+    if (lane == 0) {
+        own8[0] = ownN; own8[1] = (h.flags & NF_EXPANDED) ? 1 : 0; own8[2] = (h.flags & NF_TERMINAL) ? 1 : 0;
+        own8[3] = h.parent; own8[4] = h.parent_action; own8[5] = h.depth; own8[6] = T.n_nodes; own8[7] = 0;
+        *own_W = ownW;
+        dbaz_state pub = h;
+        pub.flags = 0; pub.depth = 0; pub.parent = -1; pub.parent_action = -1; pub.result = (int16_t)state_result(h);
+        *state_out = pub;
+    }
+}
+
 __global__ void k_tree_stats(TreeArgs ta, int32_t* __restrict__ stats8, float* __restrict__ root_W, float* __restrict__ q) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ta.n_trees) return;

@@ -716,6 +716,28 @@ class Engine:
         self._ck(self.lib.dbaz_search_root_states(self._h, _ptr(out), self._stream()))
         return out
 
+    def node_view(self, tree, node):
+        """dict of one node of one tree (include/dbaz_b200.h: dbaz_search_node), host values.  Synchronises."""
+        A, dev = self.A, self.device
+        st = torch.zeros((1, 4), dtype=torch.int64, device=dev)
+        W = torch.zeros((A,), dtype=torch.float32, device=dev)
+        N = torch.zeros((A,), dtype=torch.int32, device=dev)
+        P = torch.zeros((A,), dtype=torch.float64, device=dev)
+        ch = torch.zeros((A,), dtype=torch.int32, device=dev)
+        sg = torch.zeros((A,), dtype=torch.int32, device=dev)
+        U = torch.zeros((A,), dtype=torch.float64, device=dev)
+        own = torch.zeros((8,), dtype=torch.int32, device=dev)
+        oW = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self._ck(self.lib.dbaz_search_node(self._h, int(tree), int(node), _ptr(st), _ptr(W), _ptr(N), _ptr(P), _ptr(ch), _ptr(sg), _ptr(U),
+                                           _ptr(own), _ptr(oW), self._stream()))
+        own = own.cpu().numpy()
+        if own[7]:
+            raise IndexError("tree %d has no node %d" % (tree, node))
+        return {"state": self.states_to_numpy(st)[0], "W": W.cpu().numpy(), "visits": N.cpu().numpy(), "priors": P.cpu().numpy(),
+                "child": ch.cpu().numpy(), "sign": sg.cpu().numpy(), "ucb": U.cpu().numpy(), "N": int(own[0]), "is_expanded": bool(own[1]),
+                "is_terminal": bool(own[2]), "parent": int(own[3]), "parent_action": int(own[4]), "depth": int(own[5]),
+                "n_nodes": int(own[6]), "own_W": np.float32(oW.cpu().numpy()[0])}
+
     def tree_busy(self):
         """bool[n_games]: the tree's search is still running."""
         out = torch.empty((self.n_games,), dtype=torch.int8, device=self.device)

@@ -15,8 +15,10 @@ batching proxy needs.  Throughput comes from dotsboxesaz_b200.self_play.BatchedS
 thousands of such trees in lock-step against a device-resident net.
 
 Node objects are views: the CURRENT root reads live engine state; after init_mcts_tree() the old
-root keeps a frozen snapshot of its arrays (what self_play.get_datasets reads).  Children other
-than through init_mcts_tree are not addressable from Python.
+root keeps a frozen snapshot of its arrays (what self_play.get_datasets reads).  `node.children`
+(mcts.py:50,53-60) is a dict {action: node view} of the children that exist in the engine's node pool,
+read through dbaz_search_node; such views are valid until the tree is re-rooted (re-rooting compacts the
+pool and renumbers the nodes) and raise afterwards.
 """
 import collections
 import time
@@ -52,6 +54,7 @@ class _Tree:
     def __init__(self, dim):
         self.dim = dim
         self.eng = _acquire(dim)
+        self.epoch = 0  # bumped by every re-root: node indices of earlier views are stale then
         weakref.finalize(self, _release, dim, self.eng)
 
 
@@ -128,6 +131,14 @@ class UCTNode:
     def children_ucb_score(self):
         return self._read()["ucb"]
 
+    @property
+    def children(self):
+        """{action: child node} of the children created so far (mcts.py:50,53-60).  Only for the live root and views
+        reached from it; a root that has been re-rooted away has released its subtree (mcts.py:175 `del children`)."""
+        if self._tree is None:
+            return {}
+        return _children_of(self._tree, 0, self)
+
     def best_child(self):
         invalid = 1 - self.game_state.get_valid_moves()
         return np.argmax(-1e12 * invalid + self.children_ucb_score())
@@ -142,6 +153,50 @@ class UCTNode:
         return "\n".join(["*" * 15, "Node: " + str(self.game_state.hash), "Move: " + str(self.move),
                           "#visits: " + str(self.number_visits), "Expanded: " + str(self.is_expanded),
                           "Terminal: " + str(self.is_terminal), "Total value: " + str(self.total_value), str(self.game_state)])
+
+
+class _NodeView:
+    """A non-root node of a live tree, read on demand from the engine's node pool (dbaz_search_node).  Same read-only
+    attributes as UCTNode; valid until the tree is re-rooted."""
+
+    def __init__(self, tree, index, move, parent):
+        self._tree, self._index, self._epoch = tree, int(index), tree.epoch
+        self.move = int(move)
+        self.parent = parent
+        self.game_state = BoxesState.from_packed(self._read()["state"])
+
+    def _read(self):
+        if self._tree.epoch != self._epoch:
+            raise RuntimeError("this node view belongs to a tree that has been re-rooted since (node indices changed)")
+        return self._tree.eng.node_view(0, self._index)
+
+    is_terminal = property(lambda self: self._read()["is_terminal"])
+    is_expanded = property(lambda self: self._read()["is_expanded"])
+    child_number_visits = property(lambda self: self._read()["visits"])
+    child_total_value = property(lambda self: self._read()["W"])
+    child_priors = property(lambda self: self._read()["priors"])
+    child_player_changed = property(lambda self: self._read()["sign"])
+    number_visits = property(lambda self: self._read()["N"])
+    total_value = property(lambda self: self._read()["own_W"])
+
+    def children_ucb_score(self):
+        return self._read()["ucb"]
+
+    def best_child(self):
+        invalid = 1 - self.game_state.get_valid_moves()
+        return np.argmax(-1e12 * invalid + self.children_ucb_score())
+
+    @property
+    def children(self):
+        return _children_of(self._tree, self._index, self)
+
+    def __hash__(self):
+        return self.game_state.__hash__()
+
+
+def _children_of(tree, index, parent):
+    idx = tree.eng.node_view(0, index)["child"]
+    return {int(a): _NodeView(tree, int(idx[a]), int(a), parent) for a in np.flatnonzero(idx)}
 
 
 def create_root_uct_node(game_state):
@@ -159,6 +214,7 @@ def init_mcts_tree(previous_node, move, reuse_tree=True):
         raise RuntimeError("init_mcts_tree: this node is no longer the root of a live tree")
     previous_node._freeze()
     eng = tree.eng
+    tree.epoch += 1
     eng.advance_roots([int(move)], reuse=bool(reuse_tree))
     try:
         eng.status()
@@ -230,7 +286,10 @@ async def UCT_search(root_node, num_reads, async_nn, cpuct=(1.25, 19652), max_pe
 
 
 def print_mcts_tree(node, max_level=10, prefix=" "):
-    """Root-level summary (the reference walks the Python child dict, which does not exist here)."""
+    """mcts.py:247-272: the node, then its children recursively."""
+    if max_level < 0:
+        return
+
     def top3(arr):
         asc = max(arr) == 0
         return "; ".join(f"{i}->{arr[i]:.4f}" for i in np.argsort(arr)[::1 if asc else -1][:3])
@@ -240,3 +299,5 @@ def print_mcts_tree(node, max_level=10, prefix=" "):
     print(f"{prefix[:-1]} - child visits:{top3(node.child_number_visits)}")
     print(f"{prefix[:-1]} - priors:{top3(node.child_priors)}")
     print(f"{prefix[:-1]} - ucb:{top3(node.children_ucb_score())}")
+    for n in node.children.values():
+        print_mcts_tree(n, max_level - 1, prefix + "   |")

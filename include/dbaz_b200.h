@@ -157,6 +157,15 @@ int dbaz_search_root_children(dbaz_engine *e, float *W, double *priors, int32_t 
  * n_nodes, error}; root_W float32[n]; q float32[n] (TreeRoot.get_tree_stats, mcts.py:33-36) */
 int dbaz_search_tree_stats(dbaz_engine *e, int32_t *stats8, float *root_W, float *q, uint64_t stream);
 int dbaz_search_root_states(dbaz_engine *e, dbaz_state *out, uint64_t stream);
+/* Any node of a tree, for walks from the host (UCTNode.children[...], print_mcts_tree; mcts.py:47-65,247-272).  Node 0 is
+ * the root; child[a] (int32[A]) is the node index of the child created for action a, 0 = not created.  W float32[A],
+ * N int32[A], priors float64[A], sign int32[A], ucb float64[A] as children_ucb_score() returns them for this node;
+ * own8 int32[8] = {own N, is_expanded, is_terminal, parent node, parent action, depth, nodes in the tree, 1 if no such node};
+ * own_W float32[1]; state_out: the node's packed state.  Indices are valid until the next dbaz_search_advance_roots /
+ * dbaz_search_reset_roots of that tree (re-rooting compacts the pool). */
+int dbaz_search_node(dbaz_engine *e, int32_t tree, int32_t node, dbaz_state *state_out, float *W, int32_t *N,
+                     double *priors, int32_t *child, int32_t *sign, double *ucb, int32_t *own8, float *own_W,
+                     uint64_t stream);
 /* int8[n_games]: 1 while the tree's search is running (simulations left or a leaf waiting for the evaluator) */
 int dbaz_search_tree_busy(dbaz_engine *e, int8_t *out, uint64_t stream);
 /* init_mcts_tree (mcts.py:163-180): moves int32[n_games], -1 = leave that tree alone.  With

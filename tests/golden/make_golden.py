@@ -328,6 +328,41 @@ def gen_mcts_pending():
     return out
 
 
+def node_record(node, depth):
+    """A node of the reference's tree with its children (UCTNode.children, mcts.py:50-60), `depth` levels down."""
+    rec = {"move": None if node.move is None else int(node.move),
+           "visits": [int(x) for x in node.child_number_visits], "W": hx(node.child_total_value, np.float32),
+           "priors": hx(np.asarray(node.child_priors, dtype=np.float64), np.float64),
+           "sign": [int(x) for x in node.child_player_changed],
+           "N": int(np.asarray(node.number_visits).ravel()[0]), "own_W": float(np.asarray(node.total_value).ravel()[0]),
+           "ucb": hx(np.asarray(node.children_ucb_score(), dtype=np.float64), np.float64),
+           "is_terminal": bool(node.is_terminal), "is_expanded": bool(node.is_expanded), "state": state_record(node.game_state)}
+    if depth > 0:
+        rec["children"] = {str(a): node_record(c, depth - 1) for a, c in sorted(node.children.items())}
+    return rec
+
+
+def gen_treewalk():
+    """Trees of the reference walked from Python: root, children and grandchildren after a search (and after a re-root
+    with reuse), for UCTNode.children / print_mcts_tree of the drop-in."""
+    out = []
+    for (L, C, pre, n, kind) in ((3, 3, [0, 4, 16], 300, 0), (3, 3, [], 150, 1), (2, 2, [0, 1], 120, 0), (5, 5, [3, 40], 200, 0)):
+        set_board(L, C)
+        s = BoxesState()
+        for m in pre:
+            s.play_(int(m))
+        root = mcts.create_root_uct_node(s)
+        nn = make_nn(kind)
+        asyncio.run(mcts.UCT_search(root, n, nn, cpuct=CPUCT, max_pending_evals=1, dirichlet=(0.0, 0.0)))
+        first = node_record(root, 2)
+        mv = int(np.argmax(root.child_number_visits))
+        root = mcts.init_mcts_tree(root, mv, reuse_tree=True)
+        asyncio.run(mcts.UCT_search(root, n, nn, cpuct=CPUCT, max_pending_evals=1, dirichlet=(0.0, 0.0)))
+        out.append({"L": L, "C": C, "pre_moves": pre, "num_reads": n, "kind": kind, "first": first, "reroot_move": mv,
+                    "second": node_record(root, 2)})
+    return out
+
+
 def dump(name, obj):
     import gzip
     with gzip.GzipFile(os.path.join(OUT, name + ".json.gz"), "wb", mtime=0) as fh:
@@ -335,7 +370,7 @@ def dump(name, obj):
 
 
 def main():
-    which = sys.argv[1:] or ["games", "mcts", "selfplay", "symmetries", "mcts_pending"]
+    which = sys.argv[1:] or ["games", "mcts", "selfplay", "symmetries", "mcts_pending", "treewalk"]
     if "games" in which:
         dump("games", gen_games())
     if "mcts" in which:
@@ -346,6 +381,8 @@ def main():
         dump("symmetries", gen_symmetries())
     if "mcts_pending" in which:
         dump("mcts_pending", gen_mcts_pending())
+    if "treewalk" in which:
+        dump("treewalk", gen_treewalk())
 
 
 if __name__ == "__main__":

@@ -330,3 +330,61 @@ def test_time_limited_player(api):
     while end.get_result() is None:
         end.play_(int(end.get_valid_moves(as_indices=True)[0]))
     assert asyncio.run(player.serve_once(nn, end, 0.05)) is None
+
+
+def _cmp_node(view, rec, where):
+    """A node view of the drop-in against the reference's node (tests/golden/treewalk.json.gz): per-child arrays, own
+    N / W, UCB scores, flags, state -- bit for bit."""
+    from golden_io import unhex
+    assert view.child_number_visits.tolist() == rec["visits"], where
+    assert np.array_equal(np.asarray(view.child_total_value, dtype=np.float32), unhex(rec["W"], np.float32)), where
+    if rec["is_expanded"]:
+        assert np.array_equal(np.asarray(view.child_priors, dtype=np.float64), unhex(rec["priors"], np.float64)), where
+        assert np.array_equal(np.asarray(view.children_ucb_score(), dtype=np.float64), unhex(rec["ucb"], np.float64)), where
+        assert np.asarray(view.child_player_changed).tolist() == rec["sign"], where
+    assert int(view.number_visits) == rec["N"] and np.float32(view.total_value) == np.float32(rec["own_W"]), where
+    assert bool(view.is_terminal) == rec["is_terminal"] and bool(view.is_expanded) == rec["is_expanded"], where
+    gs, st = view.game_state, rec["state"]
+    assert bytes(gs.board.ravel().tolist()).hex() == st["board"] and gs.to_play == st["to_play"], where
+
+
+@pytest.mark.parametrize("ti", [0, 1, 2, 3])
+def test_tree_walk_from_python(api, ti, capsys):
+    """UCTNode.children / print_mcts_tree (mcts.py:50-60,247-272): the tree below the root as the reference's Python
+    objects expose it -- root, children and grandchildren after a search and after a re-root with reuse -- read from the
+    engine's node pool (dbaz_search_node)."""
+    warnings.filterwarnings("ignore")
+    from golden_io import load
+    T = load("treewalk")[ti]
+    m, BoxesState = api["mcts"], api["BoxesState"]
+    BoxesState.init_static_fields(((T["L"], T["C"]),))
+    try:
+        s = BoxesState()
+        for mv in T["pre_moves"]:
+            s.play_(int(mv))
+        root = m.create_root_uct_node(s)
+        nn = make_nn(T["kind"])
+        for phase in ("first", "second"):
+            asyncio.run(m.UCT_search(root, T["num_reads"], nn, max_pending_evals=1, dirichlet=(0.0, 0.0)))
+            rec = T[phase]
+            _cmp_node(root, rec, (ti, phase, "root"))
+            kids = root.children
+            assert sorted(kids) == sorted(int(a) for a in rec["children"])
+            for a, child in kids.items():
+                crec = rec["children"][str(a)]
+                assert child.move == a and child.parent is root
+                _cmp_node(child, crec, (ti, phase, a))
+                gk = child.children
+                assert sorted(gk) == sorted(int(b) for b in crec["children"])
+                for b, g in gk.items():
+                    _cmp_node(g, crec["children"][str(b)], (ti, phase, a, b))
+            if phase == "first":
+                m.print_mcts_tree(root, max_level=1)
+                out = capsys.readouterr().out
+                assert out.count("child visits") == 1 + len(kids)
+                stale = next(iter(kids.values()))
+                root = m.init_mcts_tree(root, T["reroot_move"], reuse_tree=True)
+                with pytest.raises(RuntimeError):
+                    _ = stale.number_visits  # node indices changed with the re-root
+    finally:
+        BoxesState.init_static_fields(((3, 3),))
