@@ -135,7 +135,25 @@ def cpu_baseline(args):
         run_cpu_sample(args, pool, workers, 1, 1000)  # warm-up: imports, torch init
         sims, wall = run_cpu_sample(args, pool, workers, args.cpu_positions, 2000)
     kind = cpu_impl()[0]
-    return {"value": sims / wall, "unit": UNIT, "cores": workers, "kind": kind,
+    extra = {}
+    if kind == "reference":
+        # BASELINE configs[0] (the reference's own CPU-runnable case) and its tree-only rate, one process each
+        from oracle import ref_driver
+        L, C = (int(x) for x in args.board.split("x"))
+        try:
+            with ctx.Pool(2) as pool:
+                game = pool.apply_async(ref_driver.worker_game, ((((L, C)), 100, 1, 0, "simple"),))
+                tree = pool.apply_async(ref_driver.worker_search, (((L, C), args.sims, 2, 7, "fake", MAX_ROOT_PLIES),))
+                gs, gdt, gn, gmoves = game.get(timeout=600)
+                ts, tdt = tree.get(timeout=600)
+            extra = {"configs0_reference_1game_100sims": {"value": gs / gdt, "unit": UNIT, "cores": 1, "games_per_hour": gn / gdt * 3600.0,
+                                                           "sample": "%d game(s) of %d moves, %d sims in %.1f s: SelfPlay.play_game of the reference, SimpleNN fp32 "
+                                                                     "on CPU behind AsyncBatchedProxy, 100 sims/move (BASELINE configs[0])" % (gn, gmoves, gs, gdt)},
+                     "tree_only_fake_net": {"value": ts / tdt, "unit": UNIT, "cores": 1,
+                                            "sample": "2 x UCT_search(%d) of the reference with the deterministic fake net (no NN, no proxy), 1 process" % args.sims}}
+        except Exception as e:  # noqa: BLE001
+            extra = {"configs0_reference_1game_100sims": {"error": repr(e)}}
+    return {**extra, "value": sims / wall, "unit": UNIT, "cores": workers, "kind": kind,
             "sample": "%d processes x %d UCT_search(%d sims) of the bench workload on %s; %d sims in %.1f s wall"
                       % (workers, args.cpu_positions, args.sims, cpu_impl_text(kind), sims, wall),
             "host_cores": os.cpu_count()}
@@ -606,7 +624,11 @@ def main():
         net_roof = None
         flops_pos = {("simple", "3x3"): 62.9e6, ("resnet", "3x3"): 47.3e6, ("resnet", "5x5"): 106.5e6}.get((args.net, args.board))
         if flops_pos and args.net != "fake":
-            eng._batch_rows = None
+            # full width -- for an evaluator whose cost is a step function of the batch (the tower kernel's tile waves) the
+            # widest batch the wave loop actually runs: the largest multiple of its quantum
+            q = int(getattr(ev, "batch_quantum", 0) or 0)
+            net_rows = args.games if (q <= 0 or q > args.games) else (args.games // q) * q
+            eng._batch_rows = None if net_rows == args.games else net_rows
             for _ in range(3):
                 ev(eng)
             torch.cuda.synchronize()
@@ -620,9 +642,11 @@ def main():
             torch.cuda.synchronize()
             net_us = a.elapsed_time(b) / 16 * 1e3
             del gnet
-            tf = args.games * flops_pos / net_us / 1e6
+            eng._batch_rows = None
+            tf = net_rows * flops_pos / net_us / 1e6
             tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-            net_roof = {"bound": "tensor", "kernel": "evaluator, %d leaves: library conv/GEMM kernels + k_nn_stem_mma + k_nn_heads" % args.games,
+            own = "k_nn_stem_mma + k_resnet_tower (tcgen05) + head GEMM (library) + k_nn_heads" if q else "library conv/GEMM kernels + k_nn_stem_mma + k_nn_heads"
+            net_roof = {"bound": "tensor", "kernel": "evaluator, %d leaves: %s" % (net_rows, own),
                         "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "us_per_batch": net_us,
                         "peak_source": "measured, sustained bf16" if peaks else "fallback", "flops_per_position": flops_pos}
         if use_cache and not args.no_ablation and world == 1:

@@ -18,7 +18,7 @@ if [ ! -f "$SRC/mcts.py" ]; then
 fi
 rm -rf "$DST"
 mkdir -p "$DST/dots_boxes" "$DST/utils"
-for f in __init__.py game.py mcts.py nn.py self_play.py; do cp "$SRC/$f" "$DST/$f"; done
+for f in __init__.py game.py mcts.py nn.py self_play.py configuration.py; do cp "$SRC/$f" "$DST/$f"; done
 for f in __init__.py dots_boxes_game.py dots_boxes_nn.py; do cp "$SRC/dots_boxes/$f" "$DST/dots_boxes/$f"; done
 for f in __init__.py proxies.py utils.py; do cp "$SRC/utils/$f" "$DST/utils/$f"; done
 chmod -R u+w "$DST"
