@@ -652,25 +652,69 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
 
         const Mask<NW> e = hdr_edges<NW>(h);
         const double c0 = cs.x, sq = cs.y;
-        double best = -INFINITY;
-        int best_a = 0x7fffffff;
+        // ---- float32 pre-pass.  The float64 score of mcts.py:91-99 costs two divisions per lane on the critical path of
+        // every level; almost always one child is ahead of the others by far more than float32 can blur.  sf approximates
+        // the real value c0 sqrt(N) prior / (n + 1) +- W / (n + 1) with |sf - exact| <= 2^-21 (|ps| + |q|) (seven
+        // roundings of relative size 2^-24 on ps, two on q, one on the sum; the float64 score itself is within 2^-50 of
+        // the real value), ef = 2^-19 (|ps| + |q|) + 2^-100 leaves a factor of four.  A child whose upper bound is below the
+        // best lower bound can neither win nor tie.  If exactly ONE child remains it is the argmax; otherwise (ties,
+        // near-ties, N = 0) the float64 scores of the remaining candidates decide, lowest action first, as before.
+        const float c0sq = __fmul_rn((float)c0, (float)sq);
+        float sf[APL], ef[APL];
+        bool legal_k[APL];
         int ncl_k[APL];  // boxes each of this lane's actions would close (decides the child's sign and who moves next)
+        float lo_max = -INFINITY;
 #pragma unroll
         for (int k = 0; k < APL; ++k) {
             const int a = lane + 32 * k;
-            const bool legal = la.real[k] && !mask_test(e, a < A ? a : 0);
-            ncl_k[k] = 0;
-            if (legal) {
-                Child c;
-                c.W = __uint_as_float(craw[k].x); c.N = (int)craw[k].y; c.prior = __uint_as_float(craw[k].z);
+            legal_k[k] = la.real[k] && !mask_test(e, a < A ? a : 0);
+            ncl_k[k] = 0; sf[k] = 0.0f; ef[k] = 0.0f;
+            if (legal_k[k]) {
                 ncl_k[k] = la.closes(k, e, a);
-                const int sign = ncl_k[k] ? 1 : -1;
-                const double prior = (depth == 0) ? rprior[k] : (double)c.prior;
-                const double sc = ucb_score<APL, NW>(c0, sq, c, prior, sign);
-                if (best_a == 0x7fffffff || sc > best) { best = sc; best_a = a; }
+                const float inv = __frcp_rn((float)((int)craw[k].y + 1));
+                const float pr = (depth == 0) ? (float)rprior[k] : __uint_as_float(craw[k].z);
+                const float ps = __fmul_rn(__fmul_rn(c0sq, inv), pr);
+                const float q = __fmul_rn(__uint_as_float(craw[k].x), inv);
+                sf[k] = ncl_k[k] ? __fadd_rn(ps, q) : __fsub_rn(ps, q);
+                ef[k] = __fmaf_rn(1.9073486328125e-6f, __fadd_rn(fabsf(ps), fabsf(q)), 7.888609052210118e-31f);
+                lo_max = fmaxf(lo_max, __fsub_rn(sf[k], ef[k]));
             }
         }
-        const int a = warp_argmax(best, best_a);  // a non-terminal node always has a legal move
+        {
+            const unsigned u = __float_as_uint(lo_max);
+            const unsigned key = (u >> 31) ? ~u : (u | 0x80000000u);  // order-preserving image of the float
+            const unsigned m = __reduce_max_sync(0xffffffffu, key);
+            lo_max = __uint_as_float((m >> 31) ? (m & 0x7fffffffu) : ~m);
+        }
+        int n_cand = 0, a_single = 0;
+        bool cand[APL];
+#pragma unroll
+        for (int k = 0; k < APL; ++k) {
+            // a node without visits of its own (a re-used root restarts at N = 0, mcts.py:169-174) ranks by value alone and
+            // its unvisited children tie at zero: no point in bounding, every legal child goes to the exact comparison
+            cand[k] = legal_k[k] && (curN == 0 || __fadd_rn(sf[k], ef[k]) >= lo_max);
+            const unsigned bal = __ballot_sync(0xffffffffu, cand[k]);
+            if (bal) { n_cand += __popc(bal); a_single = (__ffs(bal) - 1) + 32 * k; }
+        }
+        int a;
+        if (n_cand == 1) {
+            a = a_single;
+        } else {
+            double best = -INFINITY;
+            int best_a = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < APL; ++k) {
+                if (cand[k]) {
+                    Child c;
+                    c.W = __uint_as_float(craw[k].x); c.N = (int)craw[k].y; c.prior = __uint_as_float(craw[k].z);
+                    const int sign = ncl_k[k] ? 1 : -1;
+                    const double prior = (depth == 0) ? rprior[k] : (double)c.prior;
+                    const double sc = ucb_score<APL, NW>(c0, sq, c, prior, sign);
+                    if (best_a == 0x7fffffff || sc > best) { best = sc; best_a = lane + 32 * k; }
+                }
+            }
+            a = warp_argmax(best, best_a);  // a non-terminal node always has a legal move
+        }
         const int owner = a & 31, kk = a >> 5;
         int child = 0, childN = 0, ncl = 0;
         uint32_t childW = 0;
