@@ -626,7 +626,6 @@ int dbaz_search_wave_counts(dbaz_engine* e, int32_t* out4, uint64_t stream) {
 int dbaz_cache_configure(dbaz_engine* e, int32_t log2_entries) {
     if (!e) return 1;
     if (log2_entries < 0 || log2_entries > 30) return fail(e, "log2_entries must be in [0, 30]");
-    if (log2_entries > 0 && e->board.A > 88) return fail(e, "the eval cache supports boards with at most 88 actions");
     DeviceGuard guard(e->cfg.device);
     DBAZ_CK(e, cudaDeviceSynchronize());
     if (e->ta.cache) { cudaFree(e->ta.cache); e->ta.cache = nullptr; }

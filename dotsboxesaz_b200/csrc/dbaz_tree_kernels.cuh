@@ -374,17 +374,20 @@ __device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta,
 
 // ---- evaluation cache (the engine's form of AsyncBatchedProxy's LRU, utils/proxies.py:23-26,35-43).
 // Key = get_hash() = (edge set, boxes_to_close[to_play]) (dots_boxes_game.py:106-112): exactly what get_features()
-// shows the net, so a hit returns what the net would return.  The full 96-bit key sits in EVERY 16-byte cell next to
-// its 4 payload bytes and a lookup only hits when all A cells carry the probe's key; cells are written with single
+// shows the net, so a hit returns what the net would return.  A 96-bit slice of the key sits in EVERY 16-byte cell next to
+// its 4 payload bytes and a lookup only hits when all A cells carry their slice of the probe's key; cells are written with single
 // 16-byte stores, so whatever races between trees of one launch (same key: same payload; different keys on one slot:
 // mixed cells) can only turn a hit into a miss, never into a wrong evaluation.
-struct CacheKey { uint32_t k0, k1, k2; uint32_t slot; };
+// The key is 136 bits (128 edge bits for boards up to 7x7, 8 bits of 2 * boxes_to_close); a cell has room for 96, so even
+// cells carry the slice {e0 lo, e0 hi, e1 lo} and odd cells {e1 hi, btc, 0}: a hit still needs EVERY cell to carry its slice
+// of the probe's key, i.e. all 136 bits are compared (A / 2 times each).
+struct CacheKey { uint32_t k[2][3]; uint32_t slot; };
 __device__ __forceinline__ CacheKey cache_key(const TreeArgs& ta, const Hdr& h) {
     const int btc = h.to_play ? h.btc1 : h.btc0;
     CacheKey k;
-    k.k0 = (uint32_t)h.e0; k.k1 = (uint32_t)(h.e0 >> 32);
-    k.k2 = ((uint32_t)h.e1 & 0xffffffu) | (((uint32_t)btc & 0xffu) << 24);  // A <= 88: e1 has at most 24 bits
-    uint64_t x = h.e0 * 0x9E3779B97F4A7C15ull ^ ((uint64_t)k.k2 + 0x632BE59BD9B4E019ull) * 0xC2B2AE3D27D4EB4Full;
+    k.k[0][0] = (uint32_t)h.e0; k.k[0][1] = (uint32_t)(h.e0 >> 32); k.k[0][2] = (uint32_t)h.e1;
+    k.k[1][0] = (uint32_t)(h.e1 >> 32); k.k[1][1] = (uint32_t)btc & 0xffu; k.k[1][2] = 0u;
+    uint64_t x = h.e0 * 0x9E3779B97F4A7C15ull ^ (h.e1 + ((uint64_t)(btc & 0xff) << 56) + 0x632BE59BD9B4E019ull) * 0xC2B2AE3D27D4EB4Full;
     x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
     k.slot = (uint32_t)x & ta.cache_mask;
     return k;
@@ -396,6 +399,7 @@ __device__ __forceinline__ bool cache_lookup(const Board& b, const TreeArgs& ta,
     const Hdr h = unpack_hdr(in.lh0, in.lh1);
     const CacheKey key = cache_key(ta, h);
     const uint4* cells = ta.cache + (size_t)key.slot * (size_t)b.A;
+    const int par = lane & 1;  // a = lane + 32 k has the parity of the lane
     uint4 c[APL];
     bool ok = true;
 #pragma unroll
@@ -403,7 +407,7 @@ __device__ __forceinline__ bool cache_lookup(const Board& b, const TreeArgs& ta,
         const int a = lane + 32 * k;
         if (a < b.A) {
             c[k] = cells[a];
-            ok = ok && c[k].y == key.k0 && c[k].z == key.k1 && c[k].w == key.k2;
+            ok = ok && c[k].y == key.k[par][0] && c[k].z == key.k[par][1] && c[k].w == key.k[par][2];
         } else c[k] = make_uint4(0, 0, 0, 0);
     }
     if (!__all_sync(0xffffffffu, ok)) return false;
@@ -422,12 +426,13 @@ template <int APL>
 __device__ __forceinline__ void cache_insert(const Board& b, const TreeArgs& ta, const Hdr& lh, const StepInputs<APL>& in, int lane) {
     const CacheKey key = cache_key(ta, lh);
     uint4* cells = ta.cache + (size_t)key.slot * (size_t)b.A;
+    const int par = lane & 1;
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
         const int a = lane + 32 * k;
         if (a < b.A) {
             const float payload = (a == ta.cache_vcell) ? in.value : in.p[k];
-            cells[a] = make_uint4(__float_as_uint(payload), key.k0, key.k1, key.k2);
+            cells[a] = make_uint4(__float_as_uint(payload), key.k[par][0], key.k[par][1], key.k[par][2]);
         }
     }
 }

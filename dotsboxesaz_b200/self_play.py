@@ -691,8 +691,6 @@ def default_eval_cache(params):
         return int(want)
     L, C = tuple(params.game.clazz.BOARD_DIM)
     A = 2 * (L + 1) * (C + 1)
-    if A > 88:
-        return 0
     return max(16, int(np.log2((8 << 30) / (16 * A))))
 
 

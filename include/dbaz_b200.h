@@ -201,8 +201,8 @@ int dbaz_search_wave_counts(dbaz_engine *e, int32_t *out4, uint64_t stream);
  * boxes_to_close[to_play]) (dots_boxes_game.py:106-112), shared by all trees of the engine.  The step kernel
  * stores every (priors, value) the evaluator returns and, for max_pending_evals == 1 searches, completes a
  * simulation whose leaf is found in the table on the spot -- as the reference's proxy returns a cached result
- * without suspending.  Keys are compared exactly (96 bits), so a hit always returns an evaluation of the same
- * features.  log2_entries == 0 frees the table.  Synchronises the device.  Boards with A <= 88 only. */
+ * without suspending.  Keys are compared exactly (all 136 bits: 128 edge bits + the counter), so a hit always returns an
+ * evaluation of the same features.  log2_entries == 0 frees the table.  Synchronises the device. */
 int dbaz_cache_configure(dbaz_engine *e, int32_t log2_entries);
 /* Forget every entry (call after the net's weights change). */
 int dbaz_cache_clear(dbaz_engine *e, uint64_t stream);

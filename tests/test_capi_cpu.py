@@ -138,7 +138,8 @@ def test_adaptive_ladder_and_default_cache_size():
     p.self_play.eval_cache_log2 = 0
     assert self_play.default_eval_cache(p) == 0
     p2 = DotDict({"self_play": {"mcts": {}}, "game": {"clazz": G77}})
-    assert self_play.default_eval_cache(p2) == 0                   # A = 128 > 88: no table
+    k7 = self_play.default_eval_cache(p2)                          # A = 128: 2 KB per entry
+    assert k7 == 22 and (1 << k7) * 16 * 128 <= (8 << 30)
 
 
 def test_pick_rows_prefers_cheap_rungs_and_holds_the_rows():

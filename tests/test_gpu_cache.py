@@ -180,9 +180,20 @@ def test_cache_with_real_net_matches_uncached(mods):
     eng.close()
 
 
-def test_cache_rejects_large_boards(mods):
-    engine, _ = mods
-    eng = engine.Engine((6, 6), n_games=2, max_nodes=8)  # A = 98 > 88
-    with pytest.raises(engine.EngineError):
-        eng.set_eval_cache(10)
+@pytest.mark.parametrize("board", [(6, 6), (7, 7), (4, 7)])
+def test_cache_on_large_boards(mods, board):
+    """Boards with more than 88 actions (the key no longer fits 96 bits: cells carry alternating slices of the 136-bit key):
+    cached == uncached bit for bit, and the table is used."""
+    engine, oracle = mods
+    ev = engine.FakeNetEvaluator(0)
+    n, sims = 48, 150
+    plain = engine.Engine(board, n_games=n, max_nodes=4 * sims + 64)
+    roots, played = _roots(plain, n, 30, seed=11)
+    ref = _play(plain, ev, roots, sims, 3, noise_seed=5)
+    plain.close()
+    eng = engine.Engine(board, n_games=n, max_nodes=4 * sims + 64, eval_cache=12)
+    got = _play(eng, ev, roots.clone(), sims, 3, noise_seed=5, graph_waves=4, adaptive=True)
+    for m, (a, b) in enumerate(zip(ref, got)):
+        _same(a, b, (board, "move", m))
+    assert eng.status()["cache_hits"] > 0
     eng.close()
