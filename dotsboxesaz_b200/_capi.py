@@ -44,6 +44,11 @@ SYMBOLS = {
     "dbaz_search_begin": (C.c_int, [_P, _P, _I32, _P, _D, _U64]),
     "dbaz_search_step": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _U64]),
     "dbaz_search_step2": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _I32, _I32, _P, _U64]),
+    "dbaz_search_loop_build": (C.c_int, [_P, _P, _P, _P, _I32, _I32, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+    "dbaz_search_loop_pick": (C.c_int, [_P, _P, _I32, C.c_float, C.c_float, C.c_float, _I32]),
+    "dbaz_search_loop_launch": (C.c_int, [_P, _U64, _U64]),
+    "dbaz_search_loop_counts": (C.c_int, [_P, _U64, _P, _U64]),
+    "dbaz_search_loop_destroy": (None, [_P, _U64]),
     "dbaz_search_stop": (C.c_int, [_P, _U64]),
     "dbaz_search_root_visits": (C.c_int, [_P, _P, _U64]),
     "dbaz_search_root_children": (C.c_int, [_P, _P, _P, _P, _P, _U64]),

@@ -13,6 +13,7 @@
 #include "dbaz_nn_kernels.cuh"
 #include "dbaz_tree_kernels.cuh"
 #include "dbaz_tower.cuh"
+#include "dbaz_loop.cuh"
 
 using namespace dbaz;
 
@@ -535,6 +536,127 @@ int dbaz_search_step2(dbaz_engine* e, int32_t phase, int32_t buf, int32_t max_in
     DBAZ_DISPATCH(e, (k_search_step<APL, NW, true><<<grid, TREE_WARPS * 32, 0, S(stream)>>>(
                          e->board, ta, 1, priors, values, e->noise, e->coeff, planes, dtype, layout, leaf_states, nullptr)));
     return launch_ok(e, "k_search_step (phase)");
+}
+
+/* ---------------------------------------------------------- one graph per search */
+
+struct dbaz_loop {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    LoopCtl* d_ctl = nullptr;
+    int n_rungs = 0;
+};
+
+int dbaz_search_loop_build(dbaz_engine* e, const uint64_t* rung_graphs, const int32_t* rung_rows, const float* rung_us, int32_t n_rungs,
+                           int32_t max_iters, float row_margin, float undersize, float undersize_gain, float wave_overhead_us,
+                           uint64_t* loop_out) {
+    if (!e || !rung_graphs || !rung_rows || !rung_us || !loop_out) return 1;
+    if (n_rungs < 1 || n_rungs > LOOP_MAX_RUNGS) return fail(e, "dbaz_search_loop_build: 1..48 rungs");
+    for (int r = 1; r < n_rungs; ++r)
+        if (rung_rows[r] >= rung_rows[r - 1]) return fail(e, "dbaz_search_loop_build: rung rows must be strictly descending");
+    DeviceGuard guard(e->cfg.device);
+    dbaz_loop* L = new dbaz_loop();
+    L->n_rungs = n_rungs;
+    LoopCtl h;
+    memset(&h, 0, sizeof h);
+    h.n_rungs = n_rungs;
+    for (int r = 0; r < n_rungs; ++r) { h.rows[r] = rung_rows[r]; h.us[r] = rung_us[r]; }
+    h.row_margin = row_margin; h.undersize = undersize; h.undersize_gain = undersize_gain; h.wave_overhead_us = wave_overhead_us;
+    h.max_iters = max_iters > 0 ? max_iters : 1;
+#define LOOP_CK(call)                                                                   \
+    do {                                                                                \
+        cudaError_t st_ = (call);                                                       \
+        if (st_ != cudaSuccess) {                                                       \
+            if (L->exec) cudaGraphExecDestroy(L->exec);                                 \
+            if (L->graph) cudaGraphDestroy(L->graph);                                   \
+            cudaFree(L->d_ctl);                                                         \
+            delete L;                                                                   \
+            return cuda_fail(e, #call, st_);                                            \
+        }                                                                               \
+    } while (0)
+    LOOP_CK(cudaMalloc(&L->d_ctl, sizeof(LoopCtl)));
+    LOOP_CK(cudaMemcpy(L->d_ctl, &h, sizeof h, cudaMemcpyHostToDevice));
+    LOOP_CK(cudaGraphCreate(&L->graph, 0));
+    cudaGraphConditionalHandle h_while, h_switch;
+    LOOP_CK(cudaGraphConditionalHandleCreate(&h_while, L->graph, 0, 0));
+    LOOP_CK(cudaGraphConditionalHandleCreate(&h_switch, L->graph, 0, 0));
+    int* ctr = e->ta.ctr;
+    void* args[4] = {&ctr, &L->d_ctl, &h_while, &h_switch};
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof kp);
+    kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+    // begin kernel
+    cudaGraphNode_t n_begin;
+    kp.func = (void*)k_loop_begin;
+    LOOP_CK(cudaGraphAddKernelNode(&n_begin, L->graph, nullptr, 0, &kp));
+    // WHILE node
+    cudaGraphNodeParams wp = {cudaGraphNodeTypeConditional};
+    wp.type = cudaGraphNodeTypeConditional;
+    wp.conditional.handle = h_while;
+    wp.conditional.type = cudaGraphCondTypeWhile;
+    wp.conditional.size = 1;
+    cudaGraphNode_t n_while;
+    LOOP_CK(cudaGraphAddNode(&n_while, L->graph, &n_begin, 1, &wp));
+    cudaGraph_t body = wp.conditional.phGraph_out[0];
+    // SWITCH node inside the body
+    cudaGraphNodeParams sp = {cudaGraphNodeTypeConditional};
+    sp.type = cudaGraphNodeTypeConditional;
+    sp.conditional.handle = h_switch;
+    sp.conditional.type = cudaGraphCondTypeSwitch;
+    sp.conditional.size = (unsigned)n_rungs;
+    cudaGraphNode_t n_switch;
+    LOOP_CK(cudaGraphAddNode(&n_switch, body, nullptr, 0, &sp));
+    for (int r = 0; r < n_rungs; ++r) {
+        cudaGraphNode_t child;
+        LOOP_CK(cudaGraphAddChildGraphNode(&child, sp.conditional.phGraph_out[r], nullptr, 0, reinterpret_cast<cudaGraph_t>(rung_graphs[r])));
+    }
+    // decide kernel after the switch
+    cudaGraphNode_t n_decide;
+    kp.func = (void*)k_loop_decide;
+    LOOP_CK(cudaGraphAddKernelNode(&n_decide, body, &n_switch, 1, &kp));
+    LOOP_CK(cudaGraphInstantiate(&L->exec, L->graph, 0));
+#undef LOOP_CK
+    *loop_out = reinterpret_cast<uint64_t>(L);
+    return 0;
+}
+
+int dbaz_search_loop_pick(const int32_t* rung_rows, const float* rung_us, int32_t n_rungs, float undersize, float undersize_gain,
+                          float wave_overhead_us, int32_t want) {
+    if (!rung_rows || !rung_us || n_rungs < 1 || n_rungs > LOOP_MAX_RUNGS) return -1;
+    LoopCtl c;
+    memset(&c, 0, sizeof c);
+    c.n_rungs = n_rungs;
+    for (int r = 0; r < n_rungs; ++r) { c.rows[r] = rung_rows[r]; c.us[r] = rung_us[r]; }
+    c.undersize = undersize; c.undersize_gain = undersize_gain; c.wave_overhead_us = wave_overhead_us;
+    return loop_pick(&c, want);
+}
+
+int dbaz_search_loop_launch(dbaz_engine* e, uint64_t loop, uint64_t stream) {
+    if (!e || !loop) return 1;
+    dbaz_loop* L = reinterpret_cast<dbaz_loop*>(loop);
+    DeviceGuard guard(e->cfg.device);
+    DBAZ_CK(e, cudaGraphLaunch(L->exec, S(stream)));
+    return 0;
+}
+
+int dbaz_search_loop_counts(dbaz_engine* e, uint64_t loop, uint32_t* replays_out, uint64_t stream) {
+    if (!e || !loop || !replays_out) return 1;
+    dbaz_loop* L = reinterpret_cast<dbaz_loop*>(loop);
+    DeviceGuard guard(e->cfg.device);
+    // copy the per-rung replay counts out and zero them, in stream order
+    DBAZ_CK(e, cudaMemcpyAsync(replays_out, L->d_ctl->replays, (size_t)L->n_rungs * sizeof(uint32_t), cudaMemcpyDefault, S(stream)));
+    DBAZ_CK(e, cudaMemsetAsync(L->d_ctl->replays, 0, (size_t)L->n_rungs * sizeof(uint32_t), S(stream)));
+    return 0;
+}
+
+void dbaz_search_loop_destroy(dbaz_engine* e, uint64_t loop) {
+    if (!loop) return;
+    dbaz_loop* L = reinterpret_cast<dbaz_loop*>(loop);
+    if (e) cudaSetDevice(e->cfg.device);
+    if (L->exec) cudaGraphExecDestroy(L->exec);
+    if (L->graph) cudaGraphDestroy(L->graph);
+    cudaFree(L->d_ctl);
+    delete L;
 }
 
 int dbaz_search_stop(dbaz_engine* e, uint64_t stream) {

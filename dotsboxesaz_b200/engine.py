@@ -81,7 +81,13 @@ class Engine:
         self._noise_buf = None
         self._graphs = {}
         self._graph_cost = {}
-        self.n_launches = 0  # engine kernels enqueued (graph replays count the kernels they contain)
+        self._loops = {}             # one-graph-per-search loops (dbaz_search_loop_build) per ladder of captured graphs
+        self._loop_pending = []      # (event, pinned replay counts, graphs of the ladder) of launches not yet folded in
+        self._nl = 0                 # engine kernels enqueued (graph replays count the kernels they contain)
+        self._nw = 0
+        # Optional: the adaptive wave loop as ONE graph per search (WHILE / SWITCH conditional nodes, device-side rung
+        # choice): no host wait inside a search.  DBAZ_LOOP=0 keeps the host-driven loop.
+        self.device_loop = os.environ.get("DBAZ_LOOP", "1") != "0"
         self.set_planes(torch.float32, channels_last=False)
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         # lock-step scheduling state (see set_mode / run_search(adaptive=True))
@@ -92,13 +98,55 @@ class Engine:
         self._counts_host = torch.zeros((64, 4), dtype=torch.int32).pin_memory()
         self._graph_pool = None
         self._eval_us = {}           # (id(evaluator), batch rows) -> measured microseconds per evaluator call
-        self.n_waves = 0             # dbaz_search_step launches (graph replays count the waves they contain)
+        self._loop_counts_host = None
         if eval_cache:
             self.set_eval_cache(eval_cache)
 
     # ------------------------------------------------------------ plumbing
+    @property
+    def n_launches(self):
+        """Engine kernels enqueued so far (graph replays count the kernels they contain)."""
+        self._fold_loop_counts()
+        return self._nl
+
+    @n_launches.setter
+    def n_launches(self, v):
+        self._fold_loop_counts()
+        self._nl = int(v)
+
+    @property
+    def n_waves(self):
+        """dbaz_search_step launches so far (graph replays count the waves they contain)."""
+        self._fold_loop_counts()
+        return self._nw
+
+    @n_waves.setter
+    def n_waves(self, v):
+        self._fold_loop_counts()
+        self._nw = int(v)
+
+    def _fold_loop_counts(self):
+        """Replays the device-driven loops ran since the last look: their per-rung counts arrive by an asynchronous copy."""
+        while self._loop_pending:
+            ev, counts, ladder, graphs = self._loop_pending.pop(0)
+            ev.synchronize()
+            for r, c in zip(ladder, counts.tolist()):
+                launches, waves = self._graph_cost.get(id(graphs[r]), (0, 0))
+                self._nl += int(c) * launches
+                self._nw += int(c) * waves
+
+    def _drop_loops(self):
+        for loop, _, _ in self._loops.values():
+            self.lib.dbaz_search_loop_destroy(self._h, C.c_uint64(loop))
+        self._loops = {}
+
     def close(self):
         if getattr(self, "_h", None):
+            try:
+                torch.cuda.synchronize(self.device)
+                self._drop_loops()
+            except Exception:
+                pass
             self.lib.dbaz_engine_destroy(self._h)
             self._h = None
 
@@ -112,7 +160,7 @@ class Engine:
         return C.c_uint64(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _ck(self, rc, launches=1):
-        self.n_launches += launches
+        self._nl += launches
         if rc != 0:
             raise EngineError(self.lib.dbaz_last_error(self._h).decode())
 
@@ -141,6 +189,7 @@ class Engine:
         AsyncBatchedProxy's LRU (utils/proxies.py:23-26,35-43); 0 frees it.  Synchronises."""
         self._ck(self.lib.dbaz_cache_configure(self._h, int(log2_entries)), launches=0)
         self.eval_cache_log2 = int(log2_entries)
+        self._drop_loops()
         self._graphs = {}  # captured step kernels carry the table pointer
         self._graph_pool = None  # the pool dies with its last graph
 
@@ -407,7 +456,7 @@ class Engine:
         self._ck(self.lib.dbaz_search_step(self._h, _ptr(self._priors), _ptr(self._values), _ptr(self._planes_base),
                                            _DTYPE_CODE[dtype], _capi.NHWC if cl else _capi.NCHW, _ptr(self._leaf_states),
                                            _ptr(self._leaf_kind), self._stream()))
-        self.n_waves += 1
+        self._nw += 1
 
     def step2(self, phase, buf, max_inline):
         """One launch of the two-launch wave (include/dbaz_b200.h: dbaz_search_step2).  phase 1 absorbs batch buf ^ 1 and
@@ -418,7 +467,7 @@ class Engine:
                                             _ptr(self._planes_base2[dst]), _DTYPE_CODE[dtype], _capi.NHWC if cl else _capi.NCHW,
                                             _ptr(self._leaf_states2[dst]), self._stream()))
         if phase == 1:
-            self.n_waves += 1
+            self._nw += 1
 
     def step_flush(self):
         """Stop launching simulations (UCT_search's time limit) and back up the pending leaves."""
@@ -464,8 +513,8 @@ class Engine:
             per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
             for _ in range((waves + graph_waves - 1) // graph_waves):
                 g.replay()
-                self.n_launches += graph_waves * per_wave
-                self.n_waves += graph_waves
+                self._nl += graph_waves * per_wave
+                self._nw += graph_waves
         else:
             self.begin(num_reads, noise, coeff, pending)
             for _ in range(waves):
@@ -520,6 +569,13 @@ class Engine:
         ladder = self._ladder(evaluator)
         per_wave = 1 + int(getattr(evaluator, "engine_launches", 0))
         graphs = self._ladder_graphs(evaluator, graph_waves, noise, coeff)
+        if self.device_loop:
+            try:
+                return self._run_device_loop(num_reads, evaluator, noise, coeff, graphs)
+            except EngineError as exc:  # a driver that cannot build the conditional graph: the host-driven loop does the same
+                import warnings
+                warnings.warn("device-driven wave loop unavailable (%s); using the host-driven loop" % exc)
+                self.device_loop = False
         self.begin(num_reads, noise, coeff, 1)
         stream = torch.cuda.current_stream(self.device)
         events = []
@@ -548,6 +604,38 @@ class Engine:
                 # more than the busy trees.  Too small is safe (set_batch_rows: the surplus leaves wait a wave).
                 want = min(busy, int(int(slot0[2]) * self.ROW_MARGIN) + 32)
                 rows = self._pick_rows(ladder, want, id(evaluator))
+
+    def _run_device_loop(self, num_reads, evaluator, noise, coeff, graphs):
+        """The adaptive loop as ONE graph launch (include/dbaz_b200.h: dbaz_search_loop_build): a WHILE node around a
+        SWITCH over the captured rung graphs and a decision kernel; the host neither reads counters nor waits."""
+        key = id(graphs)
+        if key not in self._loops:
+            ladder = sorted(graphs, reverse=True)
+            n = len(ladder)
+            raws = (C.c_uint64 * n)(*[int(graphs[r].raw_cuda_graph()) for r in ladder])
+            rows = (C.c_int32 * n)(*ladder)
+            us = (C.c_float * n)(*[float(self._eval_us.get((id(evaluator), r), 0.0)) for r in ladder])
+            out = C.c_uint64()
+            rc = self.lib.dbaz_search_loop_build(self._h, raws, rows, us, n, 1 << 16, float(self.ROW_MARGIN), float(self.UNDERSIZE),
+                                                 float(self.UNDERSIZE_GAIN), float(self.WAVE_OVERHEAD_US), C.byref(out))
+            if rc != 0:
+                raise EngineError(self.lib.dbaz_last_error(self._h).decode())
+            self._loops[key] = (out.value, ladder, graphs)
+        loop, ladder, _ = self._loops[key]
+        self.begin(num_reads, noise, coeff, 1)
+        self._ck(self.lib.dbaz_search_loop_launch(self._h, C.c_uint64(loop), self._stream()), launches=0)
+        if self._loop_counts_host is None:
+            self._loop_counts_host = torch.zeros((32, 48), dtype=torch.int32).pin_memory()
+            self._loop_slot = 0
+        if len(self._loop_pending) >= self._loop_counts_host.shape[0] - 1:
+            self._fold_loop_counts()  # the ring of pinned slots is about to wrap
+        counts = self._loop_counts_host[self._loop_slot % self._loop_counts_host.shape[0]][:len(ladder)]
+        self._loop_slot += 1
+        self.lib.dbaz_search_loop_counts(self._h, C.c_uint64(loop), C.c_void_p(counts.data_ptr()), self._stream())
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._loop_pending.append((ev, counts, ladder, graphs))
+        self.last_schedule = None
 
     def _ladder_graphs(self, evaluator, graph_waves, noise, coeff, short_tail=True):
         """{batch rows: CUDA graph of `graph_waves` [step -> evaluator] waves} for every rung of the ladder (compact mode).
@@ -597,8 +685,8 @@ class Engine:
 
     def _count_replay(self, g):
         launches, waves = self._graph_cost.get(id(g), (0, 0))
-        self.n_launches += launches
-        self.n_waves += waves
+        self._nl += launches
+        self._nw += waves
 
     MAX_GRAPH_SETS = 6
 
@@ -606,7 +694,12 @@ class Engine:
         """Captured graphs (and the evaluators they keep alive) of configurations not used for a while are dropped,
         oldest first: a coach loop builds a new evaluator every generation."""
         while len(self._graphs) > self.MAX_GRAPH_SETS:
-            self._graphs.pop(next(iter(self._graphs)))
+            old = self._graphs.pop(next(iter(self._graphs)))[0]
+            loop = self._loops.pop(id(old), None)
+            if loop is not None:
+                torch.cuda.synchronize(self.device)
+                self._fold_loop_counts()
+                self.lib.dbaz_search_loop_destroy(self._h, C.c_uint64(loop[0]))
 
     def _mode_key(self):
         return (self.compact, self.max_inline, self.eval_cache_log2)
@@ -650,8 +743,8 @@ class Engine:
             inline *= 4 if self._batch_rows * 16 <= self.n_games else (2 if self._batch_rows * 4 <= self.n_games else 1)
         self.lib.dbaz_search_set_mode(self._h, 1 if self.compact else 0, int(inline))
         self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), int(pending), _ptr(noise), float(coeff), self._stream())
-        g = torch.cuda.CUDAGraph()
-        n0, w0 = self.n_launches, self.n_waves
+        g = torch.cuda.CUDAGraph(keep_graph=True) if self._batch_rows is not None else torch.cuda.CUDAGraph()
+        n0, w0 = self._nl, self._nw
         overlapped = bool(self.overlap and self.compact and int(pending) == 1 and graph_waves >= 2 and graph_waves % 2 == 0)
         if overlapped and self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
@@ -680,8 +773,8 @@ class Engine:
                         main.wait_stream(self._side)
                 self._buf = 0
         self._buf = 0
-        self._graph_cost[id(g)] = (self.n_launches - n0, self.n_waves - w0)  # engine kernels / waves one replay stands for
-        self.n_launches, self.n_waves = n0, w0  # capture enqueues nothing
+        self._graph_cost[id(g)] = (self._nl - n0, self._nw - w0)  # engine kernels / waves one replay stands for
+        self._nl, self._nw = n0, w0  # capture enqueues nothing
         self.lib.dbaz_search_set_batch_rows(self._h, 0)
         self.lib.dbaz_search_set_mode(self._h, 1 if self.compact else 0, int(self.max_inline))
         return g

@@ -196,6 +196,27 @@ int dbaz_search_set_batch_rows(dbaz_engine *e, int32_t rows);
  * a stale value is a safe upper bound of the next wave's rows. */
 int dbaz_search_wave_counts(dbaz_engine *e, int32_t *out4, uint64_t stream);
 
+/* ---- one CUDA graph per search: the adaptive wave loop without the host (dotsboxesaz_b200/csrc/dbaz_loop.cuh) ----
+ * rung_graphs[r]: a cudaGraph_t (not instantiated; e.g. torch.cuda.CUDAGraph(keep_graph=True).raw_cuda_graph()) holding
+ * some waves of [dbaz_search_step -> evaluator] captured with dbaz_search_set_batch_rows(rung_rows[r]); rung_rows strictly
+ * descending; rung_us[r] the measured evaluator time of that batch.  The built graph is: a begin kernel (first rung from
+ * the busy-tree count dbaz_search_begin left), a WHILE conditional node (trees still busy) around a SWITCH conditional
+ * node over the rung graphs (cloned as child graphs) and a decision kernel that reads the wave counters and picks the
+ * next rung (most rows served per microsecond; a rung up to `undersize` short when `undersize_gain` cheaper per row).
+ * max_iters bounds the replays of one launch.  Call dbaz_search_begin, then dbaz_search_loop_launch: when the launch has
+ * drained, every tree has finished its search.  dbaz_search_loop_counts copies the per-rung replay counts since the last
+ * call to replays_out (uint32[n_rungs], device or pinned host) and zeroes them, in stream order. */
+int dbaz_search_loop_build(dbaz_engine *e, const uint64_t *rung_graphs, const int32_t *rung_rows, const float *rung_us,
+                           int32_t n_rungs, int32_t max_iters, float row_margin, float undersize, float undersize_gain,
+                           float wave_overhead_us, uint64_t *loop_out);
+/* The decision rule of the loop's device kernel, callable on the host (no GPU needed): index of the rung chosen for
+ * waves expected to ask for `want` rows. */
+int dbaz_search_loop_pick(const int32_t *rung_rows, const float *rung_us, int32_t n_rungs, float undersize,
+                          float undersize_gain, float wave_overhead_us, int32_t want);
+int dbaz_search_loop_launch(dbaz_engine *e, uint64_t loop, uint64_t stream);
+int dbaz_search_loop_counts(dbaz_engine *e, uint64_t loop, uint32_t *replays_out, uint64_t stream);
+void dbaz_search_loop_destroy(dbaz_engine *e, uint64_t loop);
+
 /* ---- evaluation cache: the engine's form of AsyncBatchedProxy's LRU (utils/proxies.py:23-26,35-43) ----
  * A direct-mapped device table of 2^log2_entries entries (16*A bytes each) keyed by get_hash() = (edge set,
  * boxes_to_close[to_play]) (dots_boxes_game.py:106-112), shared by all trees of the engine.  The step kernel

@@ -171,3 +171,25 @@ def test_pick_rows_prefers_cheap_rungs_and_holds_the_rows():
     # without measurements: the smallest rung that holds the rows
     e._eval_us = {}
     assert e._pick_rows(lad, 2400, 1) == 2560
+
+
+def test_device_loop_rule_equals_the_host_rule():
+    """The rung choice of the one-graph-per-search loop (k_loop_decide -> loop_pick, csrc/dbaz_loop.cuh) is the host's
+    Engine._pick_rows: same rung for every number of rows wanted, on a measured evaluator curve with tile-wave steps and
+    on a smooth one."""
+    import ctypes as C
+    from dotsboxesaz_b200 import _capi, engine
+    lib = _capi.load()
+    e = object.__new__(engine.Engine)
+    e.n_games, e.LADDER_STEPS = 4096, 16
+    lad = e._ladder()
+    curve = {4096: 223.0, 3840: 209.2, 3584: 212.8, 3328: 181.1, 3072: 180.6, 2816: 179.3, 2560: 177.2, 2304: 146.4, 2048: 141.2,
+             1792: 138.8, 1536: 130.1, 1280: 130.0, 1024: 103.8, 768: 80.6, 512: 70.9, 256: 56.4, 128: 52.5, 64: 51.1}
+    for us in (curve, {r: 50.0 + 0.15 * r for r in lad}):
+        e._eval_us = {(1, r): us[r] for r in lad}
+        rows = (C.c_int32 * len(lad))(*lad)
+        t = (C.c_float * len(lad))(*[us[r] for r in lad])
+        for want in range(1, 4097, 7):
+            got = lib.dbaz_search_loop_pick(rows, t, len(lad), engine.Engine.UNDERSIZE, engine.Engine.UNDERSIZE_GAIN,
+                                            engine.Engine.WAVE_OVERHEAD_US, want)
+            assert lad[got] == e._pick_rows(lad, want, 1), (want, lad[got], e._pick_rows(lad, want, 1))
