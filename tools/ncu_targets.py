@@ -45,14 +45,13 @@ def rollout():
     eng.close()
 
 
-def selfplay():
+def selfplay(n=4096):
     from dotsboxesaz_b200 import self_play
     from dotsboxesaz_b200.dots_boxes.dots_boxes_nn import SimpleNN
     from dotsboxesaz_b200.nn import FusedSimpleNN
     from dotsboxesaz_b200.utils.utils import DotDict
     dev = torch.device("cuda:0")
-    n = 4096
-    eng = engine.Engine((3, 3), n_games=n, max_nodes=4096, device=dev, eval_cache=20)
+    eng = engine.Engine((3, 3), n_games=n, max_nodes=4096, device=dev, eval_cache=20 if n <= 4096 else 24)
     torch.manual_seed(0)
     ev = FusedSimpleNN(SimpleNN(board=(3, 3)), eng)
     params = DotDict({"self_play": {"reuse_mcts_tree": True, "noise": (0.8, 0.25),
@@ -86,4 +85,4 @@ def stem():
 
 
 if __name__ == "__main__":
-    {"tower": tower, "rollout": rollout, "selfplay": selfplay, "stem": stem}[sys.argv[1]]()
+    {"tower": tower, "rollout": rollout, "selfplay": selfplay, "selfplay32k": lambda: selfplay(32768), "stem": stem}[sys.argv[1]]()
