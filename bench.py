@@ -627,8 +627,10 @@ def main():
             # full width -- for an evaluator whose cost is a step function of the batch (the tower kernel's tile waves) the
             # widest batch the wave loop actually runs: the largest multiple of its quantum
             q = int(getattr(ev, "batch_quantum", 0) or 0)
-            net_rows = args.games if (q <= 0 or q > args.games) else (args.games // q) * q
-            eng._batch_rows = None if net_rows == args.games else net_rows
+            full = args.games * args.pending  # rows of a full-width wave: one per in-flight simulation
+            net_rows = full if (q <= 0 or q > full or args.pending > 1) else (full // q) * q
+            eng.pending = args.pending
+            eng._batch_rows = None if net_rows == full else net_rows
             for _ in range(3):
                 ev(eng)
             torch.cuda.synchronize()
