@@ -260,3 +260,39 @@ def _reach(og, packed, eng):
     og.s.hash_lo, og.s.hash_hi = edges[0], edges[1]
     og.s.hash_btc2 = og.s.btc2[og.s.to_play]
     return og
+
+
+def test_elo_arena_model_routing_vs_oracle():
+    """The Elo arena swaps the model on every move according to the player to move at the ROOT (self_play.py:237-239): a
+    whole search is evaluated by that player's net.  DualEvaluator with the two deterministic fake nets: every tree must end
+    with the visit counts of an oracle search that used the net owning its root -- and differ from the other net's."""
+    from dotsboxesaz_b200 import engine, self_play
+    from oracle import oracle
+    n, sims = 64, 300
+    eng = engine.Engine((3, 3), n_games=n, max_nodes=sims + 8)
+    try:
+        g = torch.Generator(device=eng.device).manual_seed(3)
+        st = eng.new_states(n)
+        for ply in range(8):
+            legal = eng.valid_moves(st).float()
+            mv = torch.multinomial(legal + 1e-9, 1, generator=g).reshape(-1).int()
+            eng.play(st, torch.where(torch.arange(n, device=eng.device) % 9 > ply, mv, torch.full_like(mv, -1)))
+        dual = self_play.DualEvaluator(engine.FakeNetEvaluator(0), engine.FakeNetEvaluator(1), eng)
+        swap = torch.arange(n, device=eng.device) % 2 == 1           # colours alternate between games, as compute_elo does
+        to_play = st.view(torch.uint8).reshape(n, 32)[:, 20].bool()
+        dual.owner.copy_(to_play ^ swap)
+        eng.reset_roots(st)
+        eng.run_search(sims, dual)
+        vis = eng.root_visits().cpu().numpy()
+        owner = dual.owner.cpu().numpy()
+        packed = eng.states_to_numpy(st)
+        differ = 0
+        for t in range(n):
+            og = _reach(oracle.OracleGame(3, 3), packed[t], eng)
+            mine = oracle.OracleTree(3, 3, og.s, kind=int(owner[t])).search(sims, cpuct=CPUCT)
+            other = oracle.OracleTree(3, 3, og.s, kind=1 - int(owner[t])).search(sims, cpuct=CPUCT)
+            assert np.array_equal(vis[t], mine), ("routing", t, int(owner[t]))
+            differ += int(not np.array_equal(mine, other))
+        assert differ > n // 2   # the two nets do lead to different searches, so the check above is not vacuous
+    finally:
+        eng.close()
