@@ -68,6 +68,7 @@ SYMBOLS = {
     "dbaz_nn_stem_mma_pack": (C.c_int, [_P, _P, _P, _I32, _U64]),
     "dbaz_nn_stem_mma": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I64, _U64]),
     "dbaz_nn_heads": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _I64, _U64]),
+    "dbaz_nn_heads_mlp": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _I64, _U64]),
     "dbaz_nn_tower_geometry": (C.c_int, [_P, _P]),
     "dbaz_nn_stem_mma_tiles": (C.c_int, [_P, _P, _P, _P, _I64, _U64]),
     "dbaz_nn_tower_planarize": (C.c_int, [_P, _P, _P, _I64, _U64]),

@@ -443,6 +443,21 @@ int dbaz_nn_heads(dbaz_engine* e, const void* logits, int32_t ld, int32_t dtype,
     return launch_ok(e, "k_nn_heads");
 }
 
+int dbaz_nn_heads_mlp(dbaz_engine* e, const void* logits, int32_t ld, int32_t dtype, int32_t n_hidden, const float* v_w,
+                      float* priors, float* values, int64_t n, uint64_t stream) {
+    if (!e || !logits || !v_w || !priors || !values) return 1;
+    if (n <= 0) return 0;
+    if (n_hidden < 1 || n_hidden > 32 || ld < e->board.A + n_hidden) return fail(e, "dbaz_nn_heads_mlp: 1 <= n_hidden <= 32 and ld >= A + n_hidden");
+    DeviceGuard guard(e->cfg.device);
+    const int A = e->board.A;
+    const int grid = blocks_for(n * 32, 256);
+    if (dtype == DBAZ_BF16) k_nn_heads_mlp<__nv_bfloat16><<<grid, 256, 0, S(stream)>>>((const __nv_bfloat16*)logits, ld, A, n_hidden, v_w, priors, values, n);
+    else if (dtype == DBAZ_F16) k_nn_heads_mlp<__half><<<grid, 256, 0, S(stream)>>>((const __half*)logits, ld, A, n_hidden, v_w, priors, values, n);
+    else if (dtype == DBAZ_F32) k_nn_heads_mlp<float><<<grid, 256, 0, S(stream)>>>((const float*)logits, ld, A, n_hidden, v_w, priors, values, n);
+    else return fail(e, "bad dtype");
+    return launch_ok(e, "k_nn_heads_mlp");
+}
+
 /* ---------------------------------------------------------- residual tower */
 
 int dbaz_nn_tower_geometry(dbaz_engine* e, int32_t* out8) {

@@ -160,6 +160,42 @@ __global__ void k_nn_heads(const T* __restrict__ logits, int ld, int A, float* _
     if (lane == 0) values[w] = tanhf((float)row[A]);
 }
 
+// The same with ResNetZero's value head finished in the kernel (nn.py:95-97): columns A .. A + n_hidden - 1 of the row are
+// the value head's hidden pre-activations (fc0 output incl. bias); value = tanh(v_w[n_hidden] + sum_j relu(h_j) * v_w[j])
+// (weights and bias of fc1 in one device vector, so that a weight reload needs no new kernel arguments).
+// n_hidden <= 32.  One warp per row.
+template <typename T>
+__global__ void k_nn_heads_mlp(const T* __restrict__ logits, int ld, int A, int n_hidden, const float* __restrict__ v_w /* [n_hidden] weights, then the bias */,
+                               float* __restrict__ priors, float* __restrict__ values, int64_t n) {
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const T* row = logits + w * ld;
+    float x[4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int a = lane + 32 * k;
+        x[k] = a < A ? (float)row[a] : -INFINITY;
+        m = fmaxf(m, x[k]);
+    }
+    float hv = (lane < n_hidden) ? fmaxf((float)row[A + lane], 0.0f) * v_w[lane] : 0.0f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        hv += __shfl_xor_sync(0xffffffffu, hv, off);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { x[k] = (lane + 32 * k < A) ? __expf(x[k] - m) : 0.0f; s += x[k]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { int a = lane + 32 * k; if (a < A) priors[w * A + a] = x[k] * inv; }
+    if (lane == 0) values[w] = tanhf(hv + v_w[n_hidden]);
+}
+
 }  // namespace dbaz
 
 namespace dbaz {

@@ -386,6 +386,16 @@ class Engine:
                                         self._stream()))
         return priors, values
 
+    def nn_heads_mlp(self, logits, n_hidden, v_w, priors=None, values=None):
+        """logits [n, ld] (policy logits | value-head hidden pre-activations) -> softmax priors, tanh(b + relu(h) . w) with
+        v_w = float32 [n_hidden + 1] (fc1's weights, then its bias)."""
+        n, ld = logits.shape
+        priors = self.priors if priors is None else priors
+        values = self.values if values is None else values
+        self._ck(self.lib.dbaz_nn_heads_mlp(self._h, _ptr(logits), ld, _DTYPE_CODE[logits.dtype], int(n_hidden), _ptr(v_w),
+                                            _ptr(priors), _ptr(values), n, self._stream()))
+        return priors, values
+
     # ------------------------------------------------- residual tower (tcgen05)
     def tower_geometry(self):
         """dict(ok, nb boards per tile, plane, tile_bytes, chunk_bytes, chunks_per_stage, channels, wp) of the fused

@@ -641,6 +641,9 @@ class FusedResNetZero(_ReloadablePlan):
         self.head_b = torch.cat([ph.fc.bias.detach(), vh.fc0.bias.detach()]).to(dtype)
         self.v_w = vh.fc1.weight.detach().to(dtype).t().contiguous()
         self.v_b = vh.fc1.bias.detach().to(dtype)
+        # fc1 of the value head finishes inside the heads kernel (Engine.nn_heads_mlp): weights then bias, float32
+        self.v_wb = torch.cat([vh.fc1.weight.detach().float().reshape(-1), vh.fc1.bias.detach().float().reshape(-1)]).contiguous() if fi <= 32 else None
+        self.fi = fi
         self.A = A
         self.ld = (A + 1 + 7) // 8 * 8
         self.logits = torch.zeros((cap, self.ld), dtype=dtype, device=dev) if _buffers else None
@@ -674,6 +677,8 @@ class FusedResNetZero(_ReloadablePlan):
 
     def _heads(self, eng, h, n):
         out = torch.addmm(self.head_b, h, self.head_w)
+        if self.v_wb is not None:
+            return eng.nn_heads_mlp(out, self.fi, self.v_wb)   # softmax + relu / fc1 / tanh of the value head in one kernel
         logits = self.logits[:n]
         logits[:, :self.A] = out[:, :self.A]
         logits[:, self.A:self.A + 1] = torch.addmm(self.v_b, F.relu(out[:, self.A:]), self.v_w)

@@ -260,6 +260,12 @@ int dbaz_nn_stem_mma(dbaz_engine *e, const dbaz_state *leaf_states, const void *
 int dbaz_nn_heads(dbaz_engine *e, const void *logits, int32_t ld, int32_t dtype, float *priors, float *values, int64_t n,
                   uint64_t stream);
 
+/* dbaz_nn_heads with ResNetZero's value head finished in the kernel (ValueHead.forward, nn.py:95-97): columns A .. A + n_hidden - 1
+ * of a row are the hidden layer's pre-activations; values = tanh(v_w[n_hidden] + sum_j relu(h_j) * v_w[j])
+ * (v_w float32[n_hidden + 1] on the device: fc1's weights, then its bias). */
+int dbaz_nn_heads_mlp(dbaz_engine *e, const void *logits, int32_t ld, int32_t dtype, int32_t n_hidden, const float *v_w,
+                      float *priors, float *values, int64_t n, uint64_t stream);
+
 /* ---- residual tower of ResNetZero as ONE persistent tcgen05 kernel (dotsboxesaz_b200/csrc/dbaz_tower.cu) ----
  * Replaces the 2 * nb_blocks conv3x3 -> BatchNorm -> ReLU (-> +x) library calls of ResNet.forward / ResBlock.forward
  * (nn.py:16-30,33-58; 20 blocks of 64 channels in configuration.py:133-155) and, optionally, the two 1x1 head
