@@ -563,6 +563,11 @@ def N_CH_OUT(model):
 
 
 class FusedResNetZero(_ReloadablePlan):
+    # Below this many leaves the library path is used even when the tower kernel is available: one tile through 41 stages
+    # is a latency floor of ~190 us whatever the batch, cuDNN's 41 small kernels take 185-205 us at 64-168 leaves
+    # (tools/tower_vs_cudnn.py on a B200: tower 0.87x at 64 leaves, 1.02x at 256, 1.35x at 1024, 2.3x at 2664, 1.76x at 15 984)
+    TOWER_MIN_ROWS = 200
+
     """Inference plan for ResNetZero (nn.py:108-122).  Here BatchNorm sits between conv and ReLU, so it folds into
     the conv's own weights (per output channel) and bias, and every conv of the tower is ONE cuDNN kernel with its
     epilogue fused: conv-bias-ReLU for conv1 of a block, conv-add-bias-ReLU (z = the block input) for conv2 -- two
@@ -648,14 +653,15 @@ class FusedResNetZero(_ReloadablePlan):
         self.ld = (A + 1 + 7) // 8 * 8
         self.logits = torch.zeros((cap, self.ld), dtype=dtype, device=dev) if _buffers else None
         self.engine_launches = (2 if (self.fused_stem is not None or self.stem_mma is not None) else 1) + (1 if self.tower is not None else 0)  # own kernels per batch: (stem,) (tower,) heads
-        if self.tower is not None:
-            self.stem_out = None  # the stem writes the tower's tiles
+        if self.tower is not None and _buffers:
+            # the stem writes the tower's tiles; the NHWC stem output only serves the library path of tiny batches
+            self.stem_out = torch.empty((min(cap, self.TOWER_MIN_ROWS), engine.rows, engine.cols, c0.out_channels), dtype=dtype, device=dev)
         engine.set_planes(dtype, channels_last=True)
 
     @torch.no_grad()
     def __call__(self, eng):
         n = eng.n_rows
-        if self.tower is not None:
+        if self.tower is not None and n >= self.TOWER_MIN_ROWS:
             # stem -> tower -> heads: the stem writes the tower's planar tiles, no NHWC activation tensor in between
             packed, bias, n_stages, hc = self.tower
             eng.nn_stem_mma_tiles(eng.leaf_states, self.stem_mma, self.tower_tiles)

@@ -191,6 +191,7 @@ def test_config3_5x5_800sims_resnet20_bf16_vs_oracle():
         model = ResNetZero(DotDict({"nn": {"model_parameters": resnet_zero_parameters((5, 5), nb_blocks=20)}}))
         plan = FusedResNetZero(model, eng, dtype=torch.bfloat16)
         assert plan.tower is not None and plan.tower[2] == 40
+        plan.TOWER_MIN_ROWS = 0  # 96 leaves per wave: keep them on the tower kernel (tiny batches default to the library path)
         ev = _LoggingEvaluator(plan, eng)
         # roots: a few random plies each, built with the engine's own rules
         g = torch.Generator(device=eng.device).manual_seed(7)
