@@ -100,16 +100,9 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 
 // Shared-memory matrix descriptor, K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices; row groups SBO
 // bytes apart, the two 16-byte K halves of one K = 16 step LBO bytes apart.  With SBO = 128 rows are 16 bytes apart
-// linearly, so `start` may point at any row.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t start, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((start >> 4) & 0x3fffu);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
-    d |= (uint64_t)((128u >> 4) & 0x3fffu) << 32;  // SBO
-    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-    return d;                                      // base offset 0, layout type 0 = no swizzle
-}
-// the same from a precomputed low word (start >> 4 | LBO >> 4 << 16): adding to it moves the start in 16-byte units
+// linearly, so the start may point at any row.  Bits: start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), descriptor
+// version 1 [46,48), base offset 0, layout type 0 (no swizzle) [61,64).
+// desc64(): the descriptor from a precomputed low word (start >> 4 | LBO >> 4 << 16): adding to it moves the start in 16-byte units
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | (uint64_t)lo; }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

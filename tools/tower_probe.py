@@ -95,10 +95,6 @@ def main():
 
 
 
-def _unused():
-    pass
-
-
 def trace(board="5x5", n_boards=None, blocks=20):
     """Timeline of CTA 0's first tile (clock64 cycles relative to the first stage)."""
     L, C = (int(v) for v in board.split("x"))
