@@ -139,10 +139,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
 // {bf16(max(hi, 0)), bf16(max(lo, 0))}: the ReLU rides in the conversion
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
     uint32_t d;
