@@ -379,9 +379,12 @@ def coach_config(args, torch, dist, rank, world, dev, board=(5, 5), games_per_ra
     params.nn.train_params.val_batch_size = 1024
     params.nn.train_params.max_samples_per_gen = 65536
     t0 = time.time()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True  # PyTorch's default, i.e. what the reference's fp32 training runs with (the search part of this file switches it off)
     try:
         timings = coach.learn_to_play(params, 0, 1)
     finally:
+        torch.backends.cudnn.allow_tf32 = tf32
         BoxesState.init_static_fields(((3, 3),))
         if rank == 0:
             shutil.rmtree(root, ignore_errors=True)
