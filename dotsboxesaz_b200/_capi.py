@@ -24,6 +24,13 @@ class Config(C.Structure):
                 ("cpuct", C.c_double), ("cpuct_base", C.c_double)]
 
 
+class SelfplayBuffers(C.Structure):
+    """dbaz_selfplay_buffers (include/dbaz_b200.h): device pointers of the asynchronous self-play loop."""
+    _fields_ = [("n_moves", C.c_int32), ("reserved", C.c_int32)] + [(k, C.c_void_p) for k in (
+        "inv_temp", "uniforms", "noise", "reads_by_k", "searching", "move_idx", "moves", "h_states", "h_visits", "h_active",
+        "h_moves", "h_stats", "h_q", "noise_buf", "reads", "left")]
+
+
 # every symbol include/dbaz_b200.h declares: name -> (restype, argtypes)
 _P, _I64, _U64, _I32, _D = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_double
 SYMBOLS = {
@@ -57,6 +64,8 @@ SYMBOLS = {
     "dbaz_search_node": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U64]),
     "dbaz_search_tree_busy": (C.c_int, [_P, _P, _U64]),
     "dbaz_search_advance_roots": (C.c_int, [_P, _P, _I32, _U64]),
+    "dbaz_selfplay_pick": (C.c_int, [_P, C.POINTER(SelfplayBuffers), _U64]),
+    "dbaz_selfplay_restart": (C.c_int, [_P, C.POINTER(SelfplayBuffers), _I32, _U64]),
     "dbaz_search_status": (C.c_int, [_P, _P, _U64]),
     "dbaz_search_set_mode": (C.c_int, [_P, _I32, _I32]),
     "dbaz_search_wave_counts": (C.c_int, [_P, _P, _U64]),

@@ -12,6 +12,7 @@
 #include "dbaz_game_kernels.cuh"
 #include "dbaz_nn_kernels.cuh"
 #include "dbaz_tree_kernels.cuh"
+#include "dbaz_selfplay.cuh"
 #include "dbaz_tower.cuh"
 #include "dbaz_loop.cuh"
 
@@ -735,6 +736,36 @@ int dbaz_search_advance_roots(dbaz_engine* e, const int32_t* moves, int32_t reus
     else k_advance_roots<2><<<e->ta.n_trees, ADV_THREADS, e->adv_smem, S(stream)>>>(e->board, e->ta, moves, reuse);
     e->noise = nullptr; e->coeff = 0.0;
     return launch_ok(e, "k_advance_roots");
+}
+
+static int selfplay_args(dbaz_engine* e, const dbaz_selfplay_buffers* b, SelfplayArgs& sp) {
+    if (!b->inv_temp || !b->uniforms || !b->reads_by_k || !b->searching || !b->move_idx || !b->moves || !b->h_states || !b->h_visits ||
+        !b->h_active || !b->h_moves || !b->h_stats || !b->h_q || !b->reads || !b->left || b->n_moves <= 0 || (b->noise && !b->noise_buf))
+        return fail(e, "dbaz_selfplay: a required buffer is NULL or n_moves <= 0");
+    sp.n_moves = b->n_moves; sp.inv_temp = b->inv_temp; sp.uniforms = b->uniforms; sp.noise = b->noise; sp.reads_by_k = b->reads_by_k;
+    sp.searching = b->searching; sp.move_idx = b->move_idx; sp.moves = b->moves; sp.h_states = b->h_states; sp.h_visits = b->h_visits;
+    sp.h_active = b->h_active; sp.h_moves = b->h_moves; sp.h_stats = b->h_stats; sp.h_q = b->h_q; sp.noise_buf = b->noise_buf;
+    sp.reads = b->reads; sp.left = b->left;
+    return 0;
+}
+
+int dbaz_selfplay_pick(dbaz_engine* e, const dbaz_selfplay_buffers* bufs, uint64_t stream) {
+    if (!e || !bufs) return 1;
+    SelfplayArgs sp;
+    if (int rc = selfplay_args(e, bufs, sp)) return rc;
+    DeviceGuard guard(e->cfg.device);
+    k_selfplay_pick<<<blocks_for(e->ta.n_trees, SP_WARPS), SP_WARPS * 32, 0, S(stream)>>>(e->board, e->ta, sp);
+    return launch_ok(e, "k_selfplay_pick");
+}
+
+int dbaz_selfplay_restart(dbaz_engine* e, const dbaz_selfplay_buffers* bufs, int32_t first, uint64_t stream) {
+    if (!e || !bufs) return 1;
+    SelfplayArgs sp;
+    if (int rc = selfplay_args(e, bufs, sp)) return rc;
+    DeviceGuard guard(e->cfg.device);
+    if (e->nw == 1) k_selfplay_restart<1><<<blocks_for(e->ta.n_trees, SP_WARPS), SP_WARPS * 32, 0, S(stream)>>>(e->board, e->ta, sp, first);
+    else k_selfplay_restart<2><<<blocks_for(e->ta.n_trees, SP_WARPS), SP_WARPS * 32, 0, S(stream)>>>(e->board, e->ta, sp, first);
+    return launch_ok(e, "k_selfplay_restart");
 }
 
 int dbaz_search_set_mode(dbaz_engine* e, int32_t compact, int32_t max_inline) {

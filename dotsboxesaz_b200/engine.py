@@ -451,7 +451,9 @@ class Engine:
         if isinstance(num_reads, int):
             self._num_reads.fill_(num_reads)
         else:
-            self._num_reads.copy_(torch.as_tensor(num_reads, dtype=torch.int32).reshape(self.n_games), non_blocking=False)
+            nr = torch.as_tensor(num_reads, dtype=torch.int32).reshape(self.n_games)
+            if not (nr.is_cuda and nr.data_ptr() == self._num_reads.data_ptr()):  # a device kernel may have filled the array in place
+                self._num_reads.copy_(nr, non_blocking=False)
         if noise is not None:
             noise = torch.as_tensor(noise, dtype=torch.float64).to(self.device).contiguous()
             if noise.shape != (self.n_games, self.A):
@@ -846,6 +848,15 @@ class Engine:
         out = torch.empty((self.n_games,), dtype=torch.int8, device=self.device)
         self._ck(self.lib.dbaz_search_tree_busy(self._h, _ptr(out), self._stream()))
         return out.bool()
+
+    def selfplay_pick(self, bufs):
+        """get_next_move + the sample of play_game (self_play.py:27-74) for every tree whose search has finished
+        (include/dbaz_b200.h: dbaz_selfplay_pick); bufs: _capi.SelfplayBuffers of device pointers."""
+        self._ck(self.lib.dbaz_selfplay_pick(self._h, C.byref(bufs), self._stream()))
+
+    def selfplay_restart(self, bufs, first=False):
+        """After advance_roots(bufs.moves): budget and noise row of the games that go on (dbaz_selfplay_restart)."""
+        self._ck(self.lib.dbaz_selfplay_restart(self._h, C.byref(bufs), 1 if first else 0, self._stream()))
 
     def advance_roots(self, moves, reuse=True):
         """init_mcts_tree (mcts.py:163-180) for every tree; moves int32[n_games], -1 = keep."""

@@ -320,7 +320,6 @@ class BatchedSelfPlay:
             temps.append(t_cur)
         inv_temp = 1.0 / torch.tensor(temps, dtype=torch.float64, device=dev)
         reads_by_k = torch.tensor([_n_searches(k, num_read) if k > 0 else 0 for k in range(n_edges + 1)], dtype=torch.int32, device=dev)
-        ar = torch.arange(n, device=dev)
         h_states = torch.zeros((n_moves, n, 4), dtype=torch.int64, device=dev)
         h_visits = torch.zeros((n_moves, n, A), dtype=torch.int32, device=dev)
         h_active = torch.zeros((n_moves, n), dtype=torch.bool, device=dev)
@@ -328,7 +327,10 @@ class BatchedSelfPlay:
         h_stats = torch.zeros((n_moves, n, 8), dtype=torch.int32, device=dev)
         h_q = torch.zeros((n_moves, n), dtype=torch.float32, device=dev)
         move_idx = torch.zeros((n,), dtype=torch.int64, device=dev)
-        leave = torch.full((n,), -3, dtype=torch.int32, device=dev)
+        searching = torch.ones((n,), dtype=torch.int8, device=dev)
+        moves = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        left_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        u_all = torch.rand((n_moves, n), dtype=torch.float64, device=dev, generator=gen)  # one uniform per (move, game): the draw of the move
 
         eng.pending = 1
         eng.set_mode(True, eng.max_inline)
@@ -339,48 +341,26 @@ class BatchedSelfPlay:
         graphs = eng._ladder_graphs(self.ev, self.graph_waves, noise_arg, coeff, short_tail=False)  # a small batch is no tail here
         ladder = eng._ladder(self.ev)
         per_wave = 1 + int(getattr(self.ev, "engine_launches", 0))
+        reads = eng._num_reads  # the array begin() hands to the engine: written in place by the restart kernel
+        from ._capi import SelfplayBuffers
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        bufs = SelfplayBuffers(n_moves=n_moves, inv_temp=ptr(inv_temp), uniforms=ptr(u_all), noise=ptr(noise_all) if alpha > 0 else None,
+                               reads_by_k=ptr(reads_by_k), searching=ptr(searching), move_idx=ptr(move_idx), moves=ptr(moves),
+                               h_states=ptr(h_states), h_visits=ptr(h_visits), h_active=ptr(h_active), h_moves=ptr(h_moves),
+                               h_stats=ptr(h_stats), h_q=ptr(h_q), noise_buf=ptr(noise_buf), reads=ptr(reads), left=ptr(left_dev))
+        keep = (bufs, inv_temp, reads_by_k, u_all, noise_all)  # the kernels hold raw pointers: these tensors live until the loop ends
 
-        def start(restart):
-            """Begin the next search of the trees in `restart` (bool[n]); the others are left alone."""
-            roots = eng.root_states()
-            valid = eng.valid_moves(roots)
-            over = eng.result(roots) != RESULT_NONE
-            restart = restart & ~over
-            mi = move_idx.clamp(max=n_moves - 1)
-            noise_buf.copy_(torch.where(restart.unsqueeze(1), noise_all[mi, ar] * valid, noise_buf))
-            reads = torch.where(restart, reads_by_k[valid.sum(1)], leave)
-            eng.begin(reads, noise_arg, coeff, 1)
-            return restart
-
-        searching = start(torch.ones((n,), dtype=torch.bool, device=dev)).clone()
-        u_all = torch.rand((n_moves, n), dtype=torch.float64, device=dev, generator=gen)  # one uniform per (move, game): the draw of the move
-        left_dev = torch.zeros((), dtype=torch.int32, device=dev)
+        eng.selfplay_restart(bufs, first=True)  # every tree begins its first search
+        eng.begin(reads, noise_arg, coeff, 1)
 
         def finish():
-            """Trees whose search has finished: record the sample, draw the move, re-root, start the next search.
-            Static shapes and in-place state only, so the whole phase is one CUDA graph."""
-            done = searching & ~eng.tree_busy()
-            roots = eng.root_states()
-            vis = eng.root_visits()
-            stats, _rw, q = eng.tree_stats()
-            v = vis.double()
-            mi = move_idx.clamp(max=n_moves - 1)
-            probs = (v / v.max(1, keepdim=True).values.clamp_min(1.0)) ** inv_temp[mi].unsqueeze(1)
-            cdf = probs.cumsum(1)
-            target = u_all[mi, ar].unsqueeze(1) * cdf[:, -1:]
-            moves = (cdf <= target).sum(1).clamp(max=A - 1).int()   # first action whose cumulative weight exceeds the target
-            moves = torch.where(done, moves, torch.full_like(moves, -1))
-            d1 = done.unsqueeze(1)
-            h_states[mi, ar] = torch.where(d1, roots, h_states[mi, ar])
-            h_visits[mi, ar] = torch.where(d1, vis, h_visits[mi, ar])
-            h_stats[mi, ar] = torch.where(d1, stats, h_stats[mi, ar])
-            h_q[mi, ar] = torch.where(done, q, h_q[mi, ar])
-            h_moves[mi, ar] = torch.where(done, moves, h_moves[mi, ar])
-            h_active[mi, ar] = h_active[mi, ar] | done
+            """Trees whose search has finished: record the sample, draw the move (k_selfplay_pick), re-root
+            (k_advance_roots), budget and noise of the next search (k_selfplay_restart), begin it (k_search_begin).
+            Four launches on in-place state, captured as one CUDA graph."""
+            eng.selfplay_pick(bufs)
             eng.advance_roots(moves, reuse=bool(sp.reuse_mcts_tree))
-            move_idx.add_(done.long())
-            searching.copy_((searching & ~done) | start(done))
-            left_dev.copy_(searching.sum().to(torch.int32))
+            eng.selfplay_restart(bufs)
+            eng.begin(reads, noise_arg, coeff, 1)
 
         torch.cuda.synchronize(dev)
         fgraph = torch.cuda.CUDAGraph()
@@ -401,7 +381,7 @@ class BatchedSelfPlay:
             slot = counts[i % 64]
             eng.lib.dbaz_search_wave_counts(eng._h, C.c_void_p(slot.data_ptr()), eng._stream())
             fgraph.replay()
-            left[i % 64].copy_(left_dev, non_blocking=True)
+            left[i % 64:i % 64 + 1].copy_(left_dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(stream)
             events.append((ev, slot, left[i % 64]))
@@ -421,7 +401,9 @@ class BatchedSelfPlay:
         self._device_hist = dict(states=list(h_states.unbind(0)), visits=list(h_visits.unbind(0)), active=list(h_active.unbind(0)),
                                  moves=list(h_moves.unbind(0)), stats=list(h_stats.unbind(0)), q=list(h_q.unbind(0)), final=final,
                                  result=res, games_idxs=games_idxs, with_features=with_features,
-                                 noise=noise_all if alpha > 0 else None)  # pre-drawn Dirichlet samples [move, game, A]
+                                 noise=noise_all if alpha > 0 else None,  # pre-drawn Dirichlet samples [move, game, A]
+                                 uniforms=u_all, inv_temp=inv_temp)              # ... and what drew the moves
+        del keep
         return info
 
     def device_samples(self):

@@ -171,6 +171,38 @@ int dbaz_search_tree_busy(dbaz_engine *e, int8_t *out, uint64_t stream);
 /* init_mcts_tree (mcts.py:163-180): moves int32[n_games], -1 = leave that tree alone.  With
  * reuse != 0 the chosen child's subtree is kept (compacted in place), else a fresh root. */
 int dbaz_search_advance_roots(dbaz_engine *e, const int32_t *moves, int32_t reuse, uint64_t stream);
+/* ---- between two searches of one game, on the device (the asynchronous self-play loop) ----
+ * SelfPlay.get_next_move (self_play.py:27-49) and the body of SelfPlay.play_game (self_play.py:51-74) for every tree whose
+ * search has finished, while the others keep searching.  All pointers are device memory of the caller; n = n_games,
+ * A = the engine's action count.  The per-move tables have n_moves rows (move index = number of moves the game has made). */
+typedef struct dbaz_selfplay_buffers {
+    int32_t n_moves;
+    int32_t reserved;
+    const double *inv_temp;    /* [n_moves] 1 / temperature at move index m (self_play.py:29-33) */
+    const double *uniforms;    /* [n_moves][n] the uniform of np.random.choice (self_play.py:35) for (move index, tree) */
+    const double *noise;       /* [n_moves][n][A] Dirichlet samples over all A entries (mcts.py:220-222); NULL: no noise */
+    const int32_t *reads_by_k; /* [A + 1] simulations of a search from a position with k legal moves (self_play.py:41-44) */
+    int8_t *searching;         /* [n] in/out: 1 while the tree's game goes on */
+    int64_t *move_idx;         /* [n] in/out: move index of the tree's current search */
+    int32_t *moves;            /* [n] out: the drawn move of a tree whose search has finished, else -1 (dbaz_search_advance_roots' input) */
+    dbaz_state *h_states;      /* [n_moves][n] history of searched roots: packed state ... */
+    int32_t *h_visits;         /* [n_moves][n][A] ... root.child_number_visits ... */
+    int8_t *h_active;          /* [n_moves][n] ... 1 where a row was recorded ... */
+    int32_t *h_moves;          /* [n_moves][n] ... the move played from it ... */
+    int32_t *h_stats;          /* [n_moves][n][8] ... dbaz_search_tree_stats' int32[8] ... */
+    float *h_q;                /* [n_moves][n] ... and q */
+    double *noise_buf;         /* [n][A] the noise array dbaz_search_begin reads: rows of restarting trees are rewritten */
+    int32_t *reads;            /* [n] out: dbaz_search_begin's num_reads (-3 = leave the tree alone) */
+    int32_t *left;             /* [1] out: games still going on after dbaz_selfplay_restart */
+} dbaz_selfplay_buffers;
+/* Trees with searching != 0 and no search in progress: the searched root goes into history row move_idx, the move is the
+ * first action whose running sum of (visits / max visits)^(1/T) exceeds uniform * total (np.random.choice's searchsorted
+ * on the cdf); moves[t] = -1 for every other tree. */
+int dbaz_selfplay_pick(dbaz_engine *e, const dbaz_selfplay_buffers *bufs, uint64_t stream);
+/* After dbaz_search_advance_roots(moves): trees with moves[t] >= 0 (all trees if first != 0, the start of a batch of
+ * games; move_idx is then not advanced) whose game goes on get reads = reads_by_k[legal moves] and their noise row times the
+ * legal mask (mcts.py:223); the others get reads = -3.  Follow with dbaz_search_begin(reads, noise_buf, ...). */
+int dbaz_selfplay_restart(dbaz_engine *e, const dbaz_selfplay_buffers *bufs, int32_t first, uint64_t stream);
 /* Synchronises `stream`.  out int64[8] = {trees with an error flag, total sims, total path nodes,
  * largest node-pool use of any tree (now or at a re-root), terminal leaves, eval-cache hits, 0, 0} (since reset_roots).  Returns non-zero (and sets
  * last_error) if any tree faulted. */

@@ -40,7 +40,9 @@ def _replay_device_history(bsp, board, num_read, games):
     q = torch.stack(h["q"]).cpu().numpy()
     noise = h["noise"].cpu().numpy() if h["noise"] is not None else None
     res = h["result"].cpu().numpy()
-    searches = sims = 0
+    uniforms = h["uniforms"].cpu().numpy() if h.get("uniforms") is not None else None
+    inv_temp = h["inv_temp"].cpu().numpy() if uniforms is not None else None
+    searches = sims = draws = 0
     for g in games:
         tree = oracle.OracleTree(L, C)
         og = oracle.OracleGame(L, C)
@@ -61,9 +63,18 @@ def _replay_device_history(bsp, board, num_read, games):
             sims += reads
             mv = int(moves[m, g])
             assert valid[mv]
+            if uniforms is not None:
+                # the draw of the move (k_selfplay_pick): np.random.choice's law, self_play.py:29-35, with the recorded uniform
+                v = visits[m, g].astype(np.float64)
+                cdf = np.cumsum((v / max(v.max(), 1.0)) ** inv_temp[m])
+                target = uniforms[m, g] * cdf[-1]
+                want = int(np.searchsorted(cdf, target, side="right"))
+                assert want == mv or abs(cdf[min(want, mv)] - target) <= 1e-12 * cdf[-1], ("draw", g, m, want, mv)
+                draws += 1
             tree.reroot(mv, reuse=True)
             og.play_(mv)
         assert og.result() == int(res[g])
+    assert uniforms is None or draws == searches
     return searches, sims
 
 
