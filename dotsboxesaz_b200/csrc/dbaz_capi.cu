@@ -5,6 +5,7 @@
 #include <numeric>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -25,6 +26,7 @@ struct dbaz_engine {
     int apl, nw;
     int n_sms;
     size_t adv_smem;
+    int adv_threads;   // threads per tree of k_advance_roots
     const double* noise;  // caller-owned device buffer of the current search (may be null)
     double coeff;
     int pending;          // max_pending_evals of the current search
@@ -222,6 +224,11 @@ int dbaz_engine_create(const dbaz_config* cfg, dbaz_engine** out) {
 
     const int nwords = (ta.max_nodes + 31) >> 5;
     e->adv_smem = (size_t)2 * nwords * 4 + (size_t)ta.max_nodes * 2;
+    // re-rooting one tree is a chain of block-wide phases: 1024 threads make it short (what the asynchronous loop of a few
+    // thousand games waits for at every check); with tens of thousands of trees the launch is bound by how many trees are
+    // resident at once, and 256 threads per tree put four times as many on an SM
+    e->adv_threads = ta.n_trees >= 16384 ? 256 : ADV_THREADS;
+    if (const char* v = getenv("DBAZ_ADV_THREADS")) { int x = atoi(v); if (x >= 32 && x <= ADV_THREADS && x % 32 == 0) e->adv_threads = x; }
     if (e->adv_smem > 48 * 1024) {
         cudaError_t s1 = cudaFuncSetAttribute(k_advance_roots<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
         cudaError_t s2 = cudaFuncSetAttribute(k_advance_roots<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
@@ -732,8 +739,8 @@ int dbaz_search_root_states(dbaz_engine* e, dbaz_state* out, uint64_t stream) {
 int dbaz_search_advance_roots(dbaz_engine* e, const int32_t* moves, int32_t reuse, uint64_t stream) {
     if (!e || !moves) return 1;
     DeviceGuard guard(e->cfg.device);
-    if (e->nw == 1) k_advance_roots<1><<<e->ta.n_trees, ADV_THREADS, e->adv_smem, S(stream)>>>(e->board, e->ta, moves, reuse);
-    else k_advance_roots<2><<<e->ta.n_trees, ADV_THREADS, e->adv_smem, S(stream)>>>(e->board, e->ta, moves, reuse);
+    if (e->nw == 1) k_advance_roots<1><<<e->ta.n_trees, e->adv_threads, e->adv_smem, S(stream)>>>(e->board, e->ta, moves, reuse);
+    else k_advance_roots<2><<<e->ta.n_trees, e->adv_threads, e->adv_smem, S(stream)>>>(e->board, e->ta, moves, reuse);
     e->noise = nullptr; e->coeff = 0.0;
     return launch_ok(e, "k_advance_roots");
 }

@@ -1073,7 +1073,7 @@ __global__ void k_reset_roots(Board b, TreeArgs ta, const dbaz_state* __restrict
 // memory); (2) prefix sum of the mark bits gives new indices; (3) nodes move front-to-back in
 // chunks of one node per warp (all loads of a chunk complete before its stores; new <= old so
 // nothing unread is overwritten), remapping parent and child indices on the fly.
-constexpr int ADV_THREADS = 1024;
+constexpr int ADV_THREADS = 1024;  // the most threads a launch may use; the launch picks 256 or 1024 (blockDim.x)
 template <int NW>
 __global__ void __launch_bounds__(ADV_THREADS)
 k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reuse) {
@@ -1081,7 +1081,7 @@ k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reu
     const int t = blockIdx.x;
     const int mv = moves[t];
     if (mv < 0) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int nwords = (ta.max_nodes + 31) >> 5;
     uint32_t* mark = smem_u32;                 // [nwords]
     uint32_t* prefix = smem_u32 + nwords;      // [nwords]
@@ -1127,8 +1127,8 @@ k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reu
             T.tree_size = reuse ? nb_visits : 0;
         }
     } else {
-        for (int w = tid; w < nwords; w += ADV_THREADS) mark[w] = 0;
-        for (int i = tid; i < n; i += ADV_THREADS) {
+        for (int w = tid; w < nwords; w += nthreads) mark[w] = 0;
+        for (int i = tid; i < n; i += nthreads) {
             int p = reinterpret_cast<const dbaz_state*>(node_ptr(ta, t, i))->parent;
             parent16[i] = (uint16_t)(p < 0 ? 0 : p);
         }
@@ -1138,7 +1138,7 @@ k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reu
         while (true) {
             if (tid == 0) s_changed = 0;
             __syncthreads();
-            for (int i = child + 1 + tid; i < n; i += ADV_THREADS) {
+            for (int i = child + 1 + tid; i < n; i += nthreads) {
                 if (!((mark[i >> 5] >> (i & 31)) & 1u)) {
                     int p = parent16[i];
                     if ((mark[p >> 5] >> (p & 31)) & 1u) { atomicOr(&mark[i >> 5], 1u << (i & 31)); s_changed = 1; }
@@ -1156,7 +1156,7 @@ k_advance_roots(Board b, TreeArgs ta, const int32_t* __restrict__ moves, int reu
         __syncthreads();
         auto newidx = [&](int i) { return (int)(prefix[i >> 5] + __popc(mark[i >> 5] & ((1u << (i & 31)) - 1u))); };
         const int pieces = ta.stride >> 4;  // 16-byte pieces per node: 2 header + A children
-        constexpr int NWARPS = ADV_THREADS / 32;
+        const int NWARPS = nthreads >> 5;
         constexpr int MAXP = (2 + DBAZ_MAX_ACTIONS + 31) / 32;
         for (int base = child; base < n; base += NWARPS) {
             const int i = base + warp;
