@@ -659,9 +659,10 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
         const double c0 = cs.x, sq = cs.y;
         // ---- float32 pre-pass.  The float64 score of mcts.py:91-99 costs two divisions per lane on the critical path of
         // every level; almost always one child is ahead of the others by far more than float32 can blur.  sf approximates
-        // the real value c0 sqrt(N) prior / (n + 1) +- W / (n + 1) with |sf - exact| <= 2^-21 (|ps| + |q|) (seven
-        // roundings of relative size 2^-24 on ps, two on q, one on the sum; the float64 score itself is within 2^-50 of
-        // the real value), ef = 2^-19 (|ps| + |q|) + 2^-100 leaves a factor of four.  A child whose upper bound is below the
+        // the real value c0 sqrt(N) prior / (n + 1) +- W / (n + 1) with |sf - exact| <= 9 * 2^-24 (|ps| + |q|) (ps: float32
+        // images of c0 and sqrt(N) and their product, the approximate reciprocal (two units), two products -- eight units of
+        // relative size 2^-24; q: three; the sum: one; the float64 score itself is within 2^-50 of the real value),
+        // ef = 2^-19 (|ps| + |q|) + 2^-100 leaves a factor of 3.5.  A child whose upper bound is below the
         // best lower bound can neither win nor tie.  If exactly ONE child remains it is the argmax; otherwise (ties,
         // near-ties, N = 0) the float64 scores of the remaining candidates decide, lowest action first, as before.
         const float c0sq = __fmul_rn((float)c0, (float)sq);
@@ -676,7 +677,8 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
             ncl_k[k] = 0; sf[k] = 0.0f; ef[k] = 0.0f;
             if (legal_k[k]) {
                 ncl_k[k] = la.closes(k, e, a);
-                const float inv = __frcp_rn((float)((int)craw[k].y + 1));
+                float inv;  // MUFU.RCP: relative error <= 2^-23 (PTX rcp.approx.f32), two units of 2^-24 in the bound above
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)((int)craw[k].y + 1)));
                 const float pr = (depth == 0) ? (float)rprior[k] : __uint_as_float(craw[k].z);
                 const float ps = __fmul_rn(__fmul_rn(c0sq, inv), pr);
                 const float q = __fmul_rn(__uint_as_float(craw[k].x), inv);
