@@ -31,6 +31,8 @@ struct dbaz_engine {
     double coeff;
     int pending;          // max_pending_evals of the current search
     int cache_log2;       // log2(entries) of the eval cache, 0 = none
+    uint32_t* d_cache_epoch;   // the table epoch the step kernels read (TreeArgs::cache_epoch)
+    uint32_t cache_epoch;      // its value after the last dbaz_cache_clear / dbaz_cache_configure
     unsigned long long* d_status;
     int* d_tower_err;     // set by k_resnet_tower when a barrier wait times out
     long long* tower_dbg; // caller-owned timeline buffer (dbaz_nn_tower_trace), may be null
@@ -264,6 +266,7 @@ void dbaz_engine_destroy(dbaz_engine* e) {
     cudaFree(e->ta.cache);
     cudaFree(e->d_status);
     cudaFree(e->d_tower_err);
+    cudaFree(e->d_cache_epoch);
     delete e;
 }
 
@@ -817,6 +820,10 @@ int dbaz_cache_configure(dbaz_engine* e, int32_t log2_entries) {
     e->ta.cache_mask = (uint32_t)(((size_t)1 << log2_entries) - 1);
     e->cache_log2 = log2_entries;
     DBAZ_CK(e, cudaMemset(e->ta.cache, 0xff, bytes));  // all-ones edges never occur (padding bits stay clear)
+    if (!e->d_cache_epoch) DBAZ_CK(e, cudaMalloc(&e->d_cache_epoch, sizeof(uint32_t)));
+    e->cache_epoch = 1;
+    DBAZ_CK(e, cudaMemcpy(e->d_cache_epoch, &e->cache_epoch, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    e->ta.cache_epoch = e->d_cache_epoch;
     return 0;
 }
 
@@ -824,9 +831,16 @@ int dbaz_cache_clear(dbaz_engine* e, uint64_t stream) {
     if (!e) return 1;
     if (!e->ta.cache) return 0;
     DeviceGuard guard(e->cfg.device);
-    const size_t bytes = ((size_t)e->ta.cache_mask + 1) * (size_t)e->board.A * sizeof(uint4);
-    DBAZ_CK(e, cudaMemsetAsync(e->ta.cache, 0xff, bytes, S(stream)));
-    return 0;
+    // every key carries the table epoch: a new epoch makes every stored entry a miss.  Only when the 32-bit epoch is about
+    // to run out is the table really wiped (8.6 GB at 2^24 entries of a 3x3 board: ~2.5 ms that a step does not have)
+    if (e->cache_epoch >= 0xfffffff0u) {
+        const size_t bytes = ((size_t)e->ta.cache_mask + 1) * (size_t)e->board.A * sizeof(uint4);
+        DBAZ_CK(e, cudaMemsetAsync(e->ta.cache, 0xff, bytes, S(stream)));
+        e->cache_epoch = 0;
+    }
+    e->cache_epoch += 1;
+    k_cache_epoch<<<1, 1, 0, S(stream)>>>(e->d_cache_epoch, e->cache_epoch);
+    return launch_ok(e, "k_cache_epoch");
 }
 
 int dbaz_search_status(dbaz_engine* e, int64_t* out8, uint64_t stream) {

@@ -105,6 +105,9 @@ struct TreeArgs {
     uint4* cache;
     uint32_t cache_mask;
     int cache_vcell;
+    // table epoch (device memory: the captured step kernels must see a later clear): part of every key, so bumping it
+    // empties the table without touching its gigabytes (dbaz_cache_clear)
+    const uint32_t* cache_epoch;
     // lock-step bookkeeping, self-resetting (the last CTA of a launch publishes and zeroes it):
     // ctr[0..1] one 64-bit word {bits 40+: rows asked for, 20-39: trees still busy, 0-19: warps done} | ctr[4] rows asked for by the last launch,
     // ctr[5] busy trees after it, ctr[6] largest ctr[4] since the host last read it, ctr[7] largest node pool use seen by a re-root
@@ -379,14 +382,14 @@ __device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta,
 // 16-byte stores, so whatever races between trees of one launch (same key: same payload; different keys on one slot:
 // mixed cells) can only turn a hit into a miss, never into a wrong evaluation.
 // The key is 136 bits (128 edge bits for boards up to 7x7, 8 bits of 2 * boxes_to_close); a cell has room for 96, so even
-// cells carry the slice {e0 lo, e0 hi, e1 lo} and odd cells {e1 hi, btc, 0}: a hit still needs EVERY cell to carry its slice
+// cells carry the slice {e0 lo, e0 hi, e1 lo} and odd cells {e1 hi, btc, table epoch}: a hit still needs EVERY cell to carry its slice
 // of the probe's key, i.e. all 136 bits are compared (A / 2 times each).
 struct CacheKey { uint32_t k[2][3]; uint32_t slot; };
 __device__ __forceinline__ CacheKey cache_key(const TreeArgs& ta, const Hdr& h) {
     const int btc = h.to_play ? h.btc1 : h.btc0;
     CacheKey k;
     k.k[0][0] = (uint32_t)h.e0; k.k[0][1] = (uint32_t)(h.e0 >> 32); k.k[0][2] = (uint32_t)h.e1;
-    k.k[1][0] = (uint32_t)(h.e1 >> 32); k.k[1][1] = (uint32_t)btc & 0xffu; k.k[1][2] = 0u;
+    k.k[1][0] = (uint32_t)(h.e1 >> 32); k.k[1][1] = (uint32_t)btc & 0xffu; k.k[1][2] = __ldg(ta.cache_epoch);
     uint64_t x = h.e0 * 0x9E3779B97F4A7C15ull ^ (h.e1 + ((uint64_t)(btc & 0xff) << 56) + 0x632BE59BD9B4E019ull) * 0xC2B2AE3D27D4EB4Full;
     x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
     k.slot = (uint32_t)x & ta.cache_mask;
@@ -1327,6 +1330,9 @@ __global__ void k_root_states(TreeArgs ta, dbaz_state* __restrict__ out) {
     h.flags = 0; h.depth = 0; h.parent = -1; h.parent_action = -1; h.result = (int16_t)state_result(h);
     out[t] = h;
 }
+
+// dbaz_cache_clear: a new epoch (never 0xffffffff, the fill value of an empty cell)
+__global__ void k_cache_epoch(uint32_t* epoch, uint32_t value) { *epoch = value; }
 
 // {errored trees, total sims, total path nodes, max n_nodes, terminal leaves} by atomics (zeroed by the host)
 __global__ void k_status(TreeArgs ta, unsigned long long* __restrict__ out4) {

@@ -257,7 +257,7 @@ void dbaz_search_loop_destroy(dbaz_engine *e, uint64_t loop);
  * without suspending.  Keys are compared exactly (all 136 bits: 128 edge bits + the counter), so a hit always returns an
  * evaluation of the same features.  log2_entries == 0 frees the table.  Synchronises the device. */
 int dbaz_cache_configure(dbaz_engine *e, int32_t log2_entries);
-/* Forget every entry (call after the net's weights change). */
+/* Forget every entry (call after the net's weights change).  O(1): the keys carry a table epoch, which this call bumps. */
 int dbaz_cache_clear(dbaz_engine *e, uint64_t stream);
 
 /* ---- leaf-evaluation pipeline: fused elementwise stages between the library GEMMs/convs ----
