@@ -334,7 +334,7 @@ def rollout_config(torch, dev, n=1 << 20, board=(5, 5)):
                "e2e": total / e2e_sec, "e2e_h2d_d2h_bytes": int(host_in.numel() * 8 * 2 + n * 4),
                "workload": "%dx%d boxes, %d concurrent games, uniformly random legal moves to the end (BASELINE configs[2])" % (board[0], board[1], n),
                "roofline": {"bound": "hbm", "kernel": "k_game_rollout", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                            "algorithmic_bytes_per_ply": 32, "note": "integer-issue bound: one thread plays a whole game in registers, HBM sees each state once in and once out"}}
+                            "algorithmic_bytes_per_ply": 32, "note": "one thread plays a whole game in registers, HBM sees each state once in and once out: the algorithmic 32 bytes per ply are SURVEY 8d's accounting, the DRAM traffic is far below it"}}
     finally:
         eng.close()
     # the reference's BoxesState on one host core, bounded sample

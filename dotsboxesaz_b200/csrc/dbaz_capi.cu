@@ -340,8 +340,8 @@ int dbaz_game_random_rollout(dbaz_engine* e, dbaz_state* states, uint64_t seed, 
     if (!e) return 1;
     if (n <= 0) return 0;
     DeviceGuard guard(e->cfg.device);
-    if (e->nw == 1) k_game_rollout<1><<<blocks_for(n, 128), 128, 0, S(stream)>>>(e->board, states, seed, game0, n_plies, moves, max_plies, n);
-    else k_game_rollout<2><<<blocks_for(n, 128), 128, 0, S(stream)>>>(e->board, states, seed, game0, n_plies, moves, max_plies, n);
+    if (e->nw == 1) k_game_rollout<1><<<blocks_for(n, 128), 128, 0, S(stream)>>>(e->board, e->ta.act_tab, states, seed, game0, n_plies, moves, max_plies, n);
+    else k_game_rollout<2><<<blocks_for(n, 128), 128, 0, S(stream)>>>(e->board, e->ta.act_tab, states, seed, game0, n_plies, moves, max_plies, n);
     return launch_ok(e, "k_game_rollout");
 }
 

@@ -45,13 +45,15 @@ struct Mask {
 
 template <int NW>
 __device__ __forceinline__ void mask_set(Mask<NW>& m, int a) {
+    // (no m.w[a >> 6]: a run-time index puts the mask -- and whatever struct holds it -- into local memory)
     if (NW == 1) m.w[0] |= 1ull << a;
-    else m.w[a >> 6] |= 1ull << (a & 63);
+    else if (a < 64) m.w[0] |= 1ull << (a & 63);
+    else m.w[NW - 1] |= 1ull << (a & 63);
 }
 template <int NW>
 __device__ __forceinline__ bool mask_test(const Mask<NW>& m, int a) {
     if (NW == 1) return (m.w[0] >> a) & 1ull;
-    return (m.w[a >> 6] >> (a & 63)) & 1ull;
+    return ((a < 64 ? m.w[0] : m.w[NW - 1]) >> (a & 63)) & 1ull;
 }
 template <int NW>
 __device__ __forceinline__ bool mask_any(const Mask<NW>& m) {
@@ -250,9 +252,20 @@ __device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint64_t game, uin
 }
 
 // index of the n-th (0-based) set bit of x; x must have more than n bits set
+// (a search over population counts: six steps whatever n is, so the threads of a warp -- one game each, every one with its
+// own n -- stay together; peeling the lowest set bit n times ran every warp for its largest n)
 __device__ __forceinline__ int nth_set_bit(uint64_t x, int n) {
-    for (int i = 0; i < n; ++i) x &= x - 1;
-    return __ffsll((long long)x) - 1;
+    uint32_t w = (uint32_t)x;
+    int pos = 0;
+    const int c0 = __popc(w);
+    if (n >= c0) { n -= c0; w = (uint32_t)(x >> 32); pos = 32; }
+    int off = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int c = __popc((w >> off) & ((1u << s) - 1u));
+        if (n >= c) { n -= c; off += s; }
+    }
+    return pos + off;
 }
 
 }  // namespace dbaz

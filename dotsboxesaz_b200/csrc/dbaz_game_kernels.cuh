@@ -71,31 +71,47 @@ __global__ void k_game_features(Board b, const dbaz_state* __restrict__ states, 
 }
 
 // Uniform random legal playout to terminal; the whole game runs in registers, HBM sees the
-// state once in and once out (plus the optional move list).
+// state once in and once out (plus the optional move list).  The state is unpacked into scalars: indexing
+// boxes_to_close by the player to move would put the whole struct into local memory (80 LDL/STL in the first version of
+// this kernel, which is what it then waited for); the two boxes an edge borders come from the engine's action table
+// (k_build_act_tab: two 16-byte loads, L1-resident) instead of being rebuilt from the geometry at every ply.
 template <int NW>
-__global__ void k_game_rollout(Board b, dbaz_state* __restrict__ states, uint64_t seed, uint64_t game0,
+__global__ void k_game_rollout(Board b, const uint4* __restrict__ act_tab, dbaz_state* __restrict__ states, uint64_t seed, uint64_t game0,
                                int32_t* __restrict__ n_plies, uint8_t* __restrict__ moves, int max_plies, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     dbaz_state s = states[i];
+    uint64_t e0 = s.edges[0], e1 = NW == 2 ? s.edges[1] : 0ull;
+    int btc0 = s.btc2[0], btc1 = s.btc2[1];   // 2 * boxes_to_close of player 0 / 1
+    int tp = s.to_play, jp = s.just_played;
+    const uint64_t real0 = b.real[0], real1 = NW == 2 ? b.real[1] : 0ull;
     int ply = 0;
-    while (state_result(s) == DBAZ_RESULT_NONE) {
-        uint64_t l0 = b.real[0] & ~s.edges[0];
-        uint64_t l1 = NW == 2 ? (b.real[1] & ~s.edges[1]) : 0ull;
-        int k0 = __popcll(l0), k = k0 + __popcll(l1);
+    // get_result() is None: not both zero, and neither player below zero (dots_boxes_game.py:51-59)
+    while ((btc0 | btc1) != 0 && btc0 >= 0 && btc1 >= 0) {
+        const uint64_t l0 = real0 & ~e0, l1 = real1 & ~e1;
+        const int k0 = __popcll(l0), k = k0 + __popcll(l1);
         if (k == 0) break;
-        uint32_t u = philox_u32(seed, game0 + (uint64_t)i, (uint32_t)ply);
-        int pick = (int)__umulhi(u, (uint32_t)k);
-        int a = pick < k0 ? nth_set_bit(l0, pick) : 64 + nth_set_bit(l1, pick - k0);
-        Mask<NW> box[2];
-        int lc[2][2];
-        action_boxes<NW>(b, a, box, lc);
-        Mask<NW> e = load_edges<NW>(s);
-        mask_set(e, a);
-        state_apply<NW>(s, a, closed_count<NW>(e, box));
+        const uint32_t u = philox_u32(seed, game0 + (uint64_t)i, (uint32_t)ply);
+        const int pick = (int)__umulhi(u, (uint32_t)k);
+        const bool low = pick < k0;
+        const int a = (low ? 0 : 64) + nth_set_bit(low ? l0 : l1, low ? pick : pick - k0);
+        if (NW == 1 || a < 64) e0 |= 1ull << (a & 63); else e1 |= 1ull << (a & 63);
+        const uint4 m0 = act_tab[2 * a], m1 = act_tab[2 * a + 1];
+        const uint64_t b00 = (uint64_t)m0.x | ((uint64_t)m0.y << 32), b01 = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
+        const uint64_t b10 = (uint64_t)m1.x | ((uint64_t)m1.y << 32), b11 = (uint64_t)m1.z | ((uint64_t)m1.w << 32);
+        int nc = 0;  // boxes the edge closes: a box mask is empty where the edge has no box on that side
+        nc += ((b00 | b01) != 0 && (e0 & b00) == b00 && (NW == 1 || (e1 & b01) == b01)) ? 1 : 0;
+        nc += ((b10 | b11) != 0 && (e0 & b10) == b10 && (NW == 1 || (e1 & b11) == b11)) ? 1 : 0;
+        jp = tp;
+        if (nc == 0) tp = 1 - tp;
+        else if (tp) btc1 -= 2 * nc; else btc0 -= 2 * nc;
         if (moves && ply < max_plies) moves[i * max_plies + ply] = (uint8_t)a;
         ++ply;
     }
+    s.edges[0] = e0;
+    if (NW == 2) s.edges[1] = e1;
+    s.btc2[0] = (int16_t)btc0; s.btc2[1] = (int16_t)btc1;
+    s.to_play = (uint8_t)tp; s.just_played = (int8_t)jp;
     states[i] = s;
     n_plies[i] = ply;
 }

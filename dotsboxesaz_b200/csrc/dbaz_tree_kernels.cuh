@@ -384,12 +384,15 @@ __device__ __forceinline__ void load_pending(const Board& b, const TreeArgs& ta,
 // The key is 136 bits (128 edge bits for boards up to 7x7, 8 bits of 2 * boxes_to_close); a cell has room for 96, so even
 // cells carry the slice {e0 lo, e0 hi, e1 lo} and odd cells {e1 hi, btc, table epoch}: a hit still needs EVERY cell to carry its slice
 // of the probe's key, i.e. all 136 bits are compared (A / 2 times each).
-struct CacheKey { uint32_t k[2][3]; uint32_t slot; };
-__device__ __forceinline__ CacheKey cache_key(const TreeArgs& ta, const Hdr& h) {
+// (k = the slice of THIS lane's cells, chosen by the lane's parity: a k[parity][3] array indexed at run time would live in
+// local memory)
+struct CacheKey { uint32_t k0, k1, k2; uint32_t slot; };
+__device__ __forceinline__ CacheKey cache_key(const TreeArgs& ta, const Hdr& h, int par) {
     const int btc = h.to_play ? h.btc1 : h.btc0;
     CacheKey k;
-    k.k[0][0] = (uint32_t)h.e0; k.k[0][1] = (uint32_t)(h.e0 >> 32); k.k[0][2] = (uint32_t)h.e1;
-    k.k[1][0] = (uint32_t)(h.e1 >> 32); k.k[1][1] = (uint32_t)btc & 0xffu; k.k[1][2] = __ldg(ta.cache_epoch);
+    k.k0 = par ? (uint32_t)(h.e1 >> 32) : (uint32_t)h.e0;
+    k.k1 = par ? ((uint32_t)btc & 0xffu) : (uint32_t)(h.e0 >> 32);
+    k.k2 = par ? __ldg(ta.cache_epoch) : (uint32_t)h.e1;
     uint64_t x = h.e0 * 0x9E3779B97F4A7C15ull ^ (h.e1 + ((uint64_t)(btc & 0xff) << 56) + 0x632BE59BD9B4E019ull) * 0xC2B2AE3D27D4EB4Full;
     x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
     k.slot = (uint32_t)x & ta.cache_mask;
@@ -400,9 +403,9 @@ __device__ __forceinline__ CacheKey cache_key(const TreeArgs& ta, const Hdr& h) 
 template <int APL>
 __device__ __forceinline__ bool cache_lookup(const Board& b, const TreeArgs& ta, StepInputs<APL>& in, int lane) {
     const Hdr h = unpack_hdr(in.lh0, in.lh1);
-    const CacheKey key = cache_key(ta, h);
-    const uint4* cells = ta.cache + (size_t)key.slot * (size_t)b.A;
     const int par = lane & 1;  // a = lane + 32 k has the parity of the lane
+    const CacheKey key = cache_key(ta, h, par);
+    const uint4* cells = ta.cache + (size_t)key.slot * (size_t)b.A;
     uint4 c[APL];
     bool ok = true;
 #pragma unroll
@@ -410,7 +413,7 @@ __device__ __forceinline__ bool cache_lookup(const Board& b, const TreeArgs& ta,
         const int a = lane + 32 * k;
         if (a < b.A) {
             c[k] = cells[a];
-            ok = ok && c[k].y == key.k[par][0] && c[k].z == key.k[par][1] && c[k].w == key.k[par][2];
+            ok = ok && c[k].y == key.k0 && c[k].z == key.k1 && c[k].w == key.k2;
         } else c[k] = make_uint4(0, 0, 0, 0);
     }
     if (!__all_sync(0xffffffffu, ok)) return false;
@@ -427,15 +430,15 @@ __device__ __forceinline__ bool cache_lookup(const Board& b, const TreeArgs& ta,
 
 template <int APL>
 __device__ __forceinline__ void cache_insert(const Board& b, const TreeArgs& ta, const Hdr& lh, const StepInputs<APL>& in, int lane) {
-    const CacheKey key = cache_key(ta, lh);
-    uint4* cells = ta.cache + (size_t)key.slot * (size_t)b.A;
     const int par = lane & 1;
+    const CacheKey key = cache_key(ta, lh, par);
+    uint4* cells = ta.cache + (size_t)key.slot * (size_t)b.A;
 #pragma unroll
     for (int k = 0; k < APL; ++k) {
         const int a = lane + 32 * k;
         if (a < b.A) {
             const float payload = (a == ta.cache_vcell) ? in.value : in.p[k];
-            cells[a] = make_uint4(__float_as_uint(payload), key.k[par][0], key.k[par][1], key.k[par][2]);
+            cells[a] = make_uint4(__float_as_uint(payload), key.k0, key.k1, key.k2);
         }
     }
 }
@@ -468,10 +471,14 @@ __device__ __forceinline__ float warp_np_sum(const float (&p)[APL], int A, int l
     for (int q = 0; q < 7; ++q) {
         const int idx = n8 + q;
         if (idx < A) {
-            float v = 0.0f;
+            float v = 0.0f;  // element idx sits on lane idx & 31 of slot idx >> 5; the slot is chosen AFTER the shuffles so that
+                             // p[] is never indexed at run time
 #pragma unroll
-            for (int k = 0; k < APL; ++k) if (k == (idx >> 5)) v = p[k];
-            r = __fadd_rn(r, __shfl_sync(0xffffffffu, v, idx & 31));
+            for (int k = 0; k < APL; ++k) {
+                const float vk = __shfl_sync(0xffffffffu, p[k], idx & 31);
+                v = (k == (idx >> 5)) ? vk : v;
+            }
+            r = __fadd_rn(r, v);
         }
     }
     return __shfl_sync(0xffffffffu, r, 0);
@@ -745,7 +752,13 @@ __device__ __forceinline__ int tree_select(const Board& b, const TreeArgs& ta, i
             childW = __shfl_sync(0xffffffffu, childW, owner);
 #pragma unroll
             for (int i = 0; i < APL; ++i)
-                if (i == (depth >> 5) && lane == (depth & 31)) { out.pe[i] = pe; out.w[i] = __uint_as_float(childW); out.n[i] = childN; }
+            {   // selects, not `if (i == ...) out.pe[i] = ...`: the compiler turns that into a run-time index and the path
+                // registers into local memory
+                const bool mine = i == (depth >> 5) && lane == (depth & 31);
+                out.pe[i] = mine ? pe : out.pe[i];
+                out.w[i] = mine ? __uint_as_float(childW) : out.w[i];
+                out.n[i] = mine ? childN : out.n[i];
+            }
         } else if (lane == 0) path[depth] = pe;
         if (child == 0) {
             // lazily create the child (mcts.py:53-54 -> BoxesState.play, dots_boxes_game.py:91-94)

@@ -362,11 +362,22 @@ class BatchedSelfPlay:
             eng.selfplay_restart(bufs)
             eng.begin(reads, noise_arg, coeff, 1)
 
-        torch.cuda.synchronize(dev)
+        # capture_begin / capture_end directly: the torch.cuda.graph() context empties the caching allocator (and the pinned
+        # host cache) on entry, after which this call's next allocations -- hundreds of MB of history and samples beside a
+        # 70 GB node arena -- go back to the driver; that cost up to a second of a three-second batch, at random
         fgraph = torch.cuda.CUDAGraph()
         l0 = eng.n_launches
-        with torch.cuda.graph(fgraph):
-            finish()
+        main = torch.cuda.current_stream(dev)
+        if eng._side is None:
+            eng._side = torch.cuda.Stream(device=dev)
+        eng._side.wait_stream(main)
+        with torch.cuda.stream(eng._side):
+            fgraph.capture_begin()
+            try:
+                finish()
+            finally:
+                fgraph.capture_end()
+        main.wait_stream(eng._side)
         finish_launches = eng.n_launches - l0  # engine kernels inside the finish graph
         eng.n_launches = l0
         stream = torch.cuda.current_stream(dev)
