@@ -130,8 +130,9 @@ __device__ __forceinline__ int closed_count(const Mask<NW>& e_after, const Mask<
 
 __device__ __forceinline__ int state_result(const dbaz_state& s) {
     if (s.btc2[0] == 0 && s.btc2[1] == 0) return 0;
-    if (s.btc2[s.to_play] < 0) return 1;
-    if (s.btc2[1 - s.to_play] < 0) return -1;
+    const int mine = s.to_play ? s.btc2[1] : s.btc2[0], other = s.to_play ? s.btc2[0] : s.btc2[1];
+    if (mine < 0) return 1;
+    if (other < 0) return -1;
     return DBAZ_RESULT_NONE;
 }
 
@@ -143,13 +144,15 @@ __device__ __forceinline__ void state_apply(dbaz_state& s, int a, int n_closed) 
     store_edges<NW>(s, e);
     s.just_played = (int8_t)s.to_play;
     if (n_closed == 0) s.to_play = 1 - s.to_play;
-    else s.btc2[s.to_play] = (int16_t)(s.btc2[s.to_play] - 2 * n_closed);
+    else if (s.to_play) s.btc2[1] = (int16_t)(s.btc2[1] - 2 * n_closed);
+    else s.btc2[0] = (int16_t)(s.btc2[0] - 2 * n_closed);
 }
 
 template <int NW>
 __device__ __forceinline__ bool state_legal(const Board& b, const dbaz_state& s, int a) {
     if (a < 0 || a >= b.A) return false;
-    uint64_t real = b.real[NW == 1 ? 0 : (a >> 6)], ed = s.edges[NW == 1 ? 0 : (a >> 6)];
+    const bool lo = NW == 1 || a < 64;  // selects: a run-time index would put the state into local memory
+    uint64_t real = lo ? b.real[0] : b.real[1], ed = lo ? s.edges[0] : s.edges[1];
     return ((real & ~ed) >> (a & 63)) & 1ull;
 }
 
