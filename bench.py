@@ -70,6 +70,9 @@ def parse_args():
     ap.add_argument("--selfplay-nodes", type=int, default=4096, help="node pool per tree of the self-play engine (tree reuse)")
     ap.add_argument("--selfplay-mode", default="async", choices=["async", "lockstep"],
                     help="async: every game at its own pace (BatchedSelfPlay.play_games_async); lockstep: all games move together")
+    ap.add_argument("--selfplay-eval-cache", type=int, default=-1,
+                    help="log2(entries) of the self-play engine's eval cache; -1 = sized for the engine "
+                         "(self_play.eval_cache_log2_for: 2^27 entries for 32768 games of 3x3 on a B200)")
     ap.add_argument("--selfplay-games", type=int, default=32768,
                     help="concurrent games per GPU of the games/hour measurement (the sims/s workload stays at --games)")
     ap.add_argument("--no-configs", action="store_true",
@@ -693,7 +696,11 @@ def main():
         sp_nodes = args.selfplay_nodes if eng_A <= 32 else max(args.selfplay_nodes, 6144)
         fit = int(80e9 // (sp_nodes * node_bytes))
         sp_games = max(256, min(args.selfplay_games, fit // 1024 * 1024 if fit >= 1024 else fit))
-        eng_sp = engine.Engine((L, C), n_games=sp_games, max_nodes=sp_nodes, device=dev, eval_cache=use_cache)
+        sp_cache = use_cache
+        if use_cache and args.selfplay_eval_cache != 0:
+            sp_cache = (args.selfplay_eval_cache if args.selfplay_eval_cache > 0
+                        else max(use_cache, sp_mod.eval_cache_log2_for(eng_A, sp_games, sp_nodes, dev)))
+        eng_sp = engine.Engine((L, C), n_games=sp_games, max_nodes=sp_nodes, device=dev, eval_cache=sp_cache)
         eng_sp.set_mode(False, args.max_inline)
         eng_sp.LADDER_STEPS = args.ladder_steps
         if args.net_plan != "fused":
@@ -734,7 +741,7 @@ def main():
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         selfplay = {"games_per_hour": sp_games * world / float(sec[0]) * 3600.0, "games": sp_games * world,
                     "seconds": float(sec[0]), "sims_per_sec": float(tot[0]) / float(sec[0]), "sample_rows": int(tot[1]),
-                    "cache_hit_frac": info["cache_hits"] / max(1, info["sims"]),
+                    "cache_hit_frac": info["cache_hits"] / max(1, info["sims"]), "eval_cache_log2": int(sp_cache),
                     "terminal_leaf_frac": info["terminal_leaves"] / max(1, info["sims"]),
                     "what": "%d concurrent games per GPU played to the end (%s), tree reuse, temperature {0: 1.0, 12: 0.02}, "
                             "samples copied to the host inside the timed region"

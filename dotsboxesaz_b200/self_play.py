@@ -673,17 +673,37 @@ def gather_samples(df, dst=0):
     return pd.concat(out).sort_index()
 
 
-def default_eval_cache(params):
-    """log2(entries) of the engine's eval cache: `params.self_play.eval_cache_log2` if given (0 = none), else up to
-    8 GB worth (3x3: 2^24 entries of 512 bytes, the table bench.py runs with; a direct-mapped table wants several slots
-    per insert) -- the role of the reference's `nn.max_cache_size` LRU (self_play.py:226-230).  (Only searches with one
-    simulation in flight per tree use the table; generate_games builds its engine that way.)"""
+def eval_cache_log2_for(A, n_slots, max_nodes, device=None):
+    """log2(entries) of the eval cache for an engine of `n_slots` trees that plays whole games: about 4096 slots per tree
+    (a direct-mapped table wants a few slots per insert; measured on 3x3 with 32 768 games per GPU: 2^24 entries 38.7 M
+    games/h, 2^25 41.0 M, 2^26 43.2 M, 2^27 45.2 M -- a game inserts ~900 positions, most of them shared with other games),
+    within 40 % of the device's memory and what the node pools leave free.  Emptying the table costs nothing (a table
+    epoch), so its size only costs memory."""
+    cell = 16 * int(A)
+    budget = 8 << 30
+    try:
+        total = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).total_memory
+        pools = int(n_slots) * int(max_nodes) * (32 + cell)
+        budget = max(1 << 30, min(int(0.4 * total), total - pools - (24 << 30)))
+    except Exception:  # no device to ask (CPU-only import): the conservative 8 GB
+        pass
+    want = max(1, 4096 * int(n_slots))
+    return max(16, min(int(np.log2(budget / cell)), int(np.ceil(np.log2(want)))))
+
+
+def default_eval_cache(params, n_slots=None, max_nodes=None, device=None):
+    """log2(entries) of the engine's eval cache: `params.self_play.eval_cache_log2` if given (0 = none), else sized for
+    the engine (eval_cache_log2_for) -- or, without an engine size, up to 8 GB worth (3x3: 2^24 entries of 512 bytes) --
+    the role of the reference's `nn.max_cache_size` LRU (self_play.py:226-230).  (Only searches with one simulation in
+    flight per tree use the table; generate_games builds its engine that way.)"""
     sp = params.self_play
     want = sp.get("eval_cache_log2", None)
     if want is not None:
         return int(want)
     L, C = tuple(params.game.clazz.BOARD_DIM)
     A = 2 * (L + 1) * (C + 1)
+    if n_slots:
+        return eval_cache_log2_for(A, n_slots, max_nodes or 8192, device)
     return max(16, int(np.log2((8 << 30) / (16 * A))))
 
 
@@ -694,9 +714,9 @@ def shard_engine(params, n_shard_games, device=None):
     cap = int(params.self_play.get("concurrent_games", 4096) or 4096)
     n_chunks = max(1, -(-int(n_shard_games) // cap))
     slots = max(1, -(-int(n_shard_games) // n_chunks))  # equal chunks: the last one is short by less than n_chunks games
-    return _engine.Engine(tuple(params.game.clazz.BOARD_DIM), n_games=slots,
-                          max_nodes=int(params.self_play.get("max_nodes_per_tree", 8192) or 8192),
-                          eval_cache=default_eval_cache(params), device=device)
+    max_nodes = int(params.self_play.get("max_nodes_per_tree", 8192) or 8192)
+    return _engine.Engine(tuple(params.game.clazz.BOARD_DIM), n_games=slots, max_nodes=max_nodes,
+                          eval_cache=default_eval_cache(params, slots, max_nodes, device), device=device)
 
 
 def game_seed(base_seed, generation, game_idx):

@@ -102,6 +102,11 @@ def test_dataset_frame_matches_reference_columns():
     assert np.array_equal(flat.to_numpy(dtype=np.float64), ref)
 
 
+def torch_has_cuda():
+    import torch
+    return torch.cuda.is_available()
+
+
 def test_adaptive_ladder_and_default_cache_size():
     """Host logic of the adaptive wave loop that needs no GPU: the batch ladder (Engine._ladder) and the default eval
     cache size (self_play.default_eval_cache)."""
@@ -140,6 +145,13 @@ def test_adaptive_ladder_and_default_cache_size():
     p2 = DotDict({"self_play": {"mcts": {}}, "game": {"clazz": G77}})
     k7 = self_play.default_eval_cache(p2)                          # A = 128: 2 KB per entry
     assert k7 == 22 and (1 << k7) * 16 * 128 <= (8 << 30)
+    # sized for an engine: ~4096 slots per tree, never more than the memory budget (8 GB when there is no device to ask)
+    p3 = DotDict({"self_play": {"mcts": {}}, "game": {"clazz": G33}})
+    assert self_play.default_eval_cache(p3, 64, 1024) == 18        # 64 trees: 2^18 entries
+    assert self_play.default_eval_cache(p3, 1024, 4096) == 22
+    assert self_play.eval_cache_log2_for(32, 1, 64) == 16           # floor
+    big = self_play.eval_cache_log2_for(32, 32768, 4096)
+    assert 24 <= big <= 27 and (big == 24 or torch_has_cuda())
 
 
 def test_pick_rows_prefers_cheap_rungs_and_holds_the_rows():
