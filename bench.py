@@ -63,7 +63,10 @@ def parse_args():
                     help="log2(entries) of the device eval cache (the reference's LRU of net outputs, utils/proxies.py:23-26); "
                          "emptied at the start of EVERY step, inside the timed region; 0 = off")
     ap.add_argument("--no-adaptive", action="store_true", help="fixed number of full-width waves instead of the adaptive loop")
-    ap.add_argument("--max-inline", type=int, default=4, help="bound on simulations per tree and wave finished without the net")
+    ap.add_argument("--max-inline", type=int, default=4, help="bound on simulations per tree and wave finished without the net "
+                                                              "(by count; the captured wave loops bound them by time, --chain-us)")
+    ap.add_argument("--chain-us", type=int, default=-1, help="time bound of the in-kernel chains in microseconds (0 = by count only; "
+                                                             "-1 = the engine's default, 20)")
     ap.add_argument("--ladder-steps", type=int, default=16, help="evaluator batch sizes of the adaptive loop: games * k / steps")
     ap.add_argument("--no-ablation", action="store_true", help="skip the extra no-cache measurement")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the games/hour measurement (whole self-play games)")
@@ -482,6 +485,8 @@ def main():
     eng = engine.Engine((L, C), n_games=args.games, max_nodes=args.sims + 8, device=dev, max_pending=args.pending,
                         eval_cache=use_cache)
     eng.set_mode(False, args.max_inline)
+    if args.chain_us >= 0:
+        eng.chain_us = args.chain_us
     eng.LADDER_STEPS = args.ladder_steps
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.net_dtype]
     if args.net == "fake":
@@ -495,6 +500,7 @@ def main():
         else:
             ev = DeviceEvaluator(model, eng, dtype=dt, channels_last=True)
 
+    eng_chain_us = int(eng.chain_us)
     roots = synthetic_roots(eng, torch, seed=1234 + rank)
     valid_np = eng.valid_moves(roots).cpu().numpy()
     rs = np.random.RandomState(99 + rank)
@@ -589,6 +595,10 @@ def main():
         eng.reset_roots(roots)
         eng.clear_eval_cache()
         eng.set_mode(adaptive, args.max_inline)
+        timed_chains = adaptive and eng.chain_us > 0 and args.max_inline > 0 and args.pending == 1
+        if timed_chains:  # the kernel the captured wave loop runs: chains bounded by time, the count only a cap
+            eng.set_mode(adaptive, eng.CHAIN_COUNT_CAP)
+            eng.set_chain_budget(eng.chain_us)
         eng.begin(args.sims, noise_dev, NOISE[1], pending=args.pending)
         evs = []
         n_waves = 2 + max(0, -(-(args.sims - min(args.pending, eng.A)) // args.pending))
@@ -604,6 +614,9 @@ def main():
                 break
         eng.step()
         torch.cuda.synchronize()
+        if timed_chains:
+            eng.set_chain_budget(0)
+            eng.set_mode(adaptive, args.max_inline)
         n_run = len(evs)
         evs = evs[min(16, n_run // 4):]
         k_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
@@ -702,6 +715,8 @@ def main():
                         else max(use_cache, sp_mod.eval_cache_log2_for(eng_A, sp_games, sp_nodes, dev)))
         eng_sp = engine.Engine((L, C), n_games=sp_games, max_nodes=sp_nodes, device=dev, eval_cache=sp_cache)
         eng_sp.set_mode(False, args.max_inline)
+        if args.chain_us >= 0:
+            eng_sp.chain_us = args.chain_us
         eng_sp.LADDER_STEPS = args.ladder_steps
         if args.net_plan != "fused":
             ev_sp = DeviceEvaluator(model, eng_sp, dtype=dt, channels_last=True)
@@ -785,7 +800,8 @@ def main():
                 "config": {"workload": workload_name(args), "board": args.board, "games_per_gpu": args.games,
                            "sims_per_move": args.sims, "net": args.net, "net_dtype": args.net_dtype, "net_plan": args.net_plan, "max_pending_evals": args.pending,
                            "eval_cache": ("2^%d entries, emptied at the start of every step" % use_cache) if use_cache else "off",
-                           "wave_loop": "adaptive (compact rows, batch ladder)" if adaptive else "fixed", "parallelism": "games sharded by index x%d, no collective" % world,
+                           "wave_loop": ("adaptive (compact rows, batch ladder, in-kernel chains bounded at %d us)" % eng_chain_us if (adaptive and eng_chain_us > 0)
+                                         else "adaptive (compact rows, batch ladder)") if adaptive else "fixed", "parallelism": "games sharded by index x%d, no collective" % world,
                            "l2": "inputs larger than L2: node pool touched per step %.2f GB/GPU vs 126 MB L2" % (
                                args.games * (args.sims + 1) * node_bytes / 1e9),
                            "graph_waves": args.graph_waves},

@@ -778,6 +778,15 @@ int dbaz_selfplay_restart(dbaz_engine* e, const dbaz_selfplay_buffers* bufs, int
     return launch_ok(e, "k_selfplay_restart");
 }
 
+int dbaz_search_set_chain_budget(dbaz_engine* e, int32_t microseconds) {
+    if (!e) return 1;
+    if (microseconds < 0 || microseconds > 100000) return fail(e, "chain budget must be in [0, 100000] microseconds");
+    int khz = 0;
+    DBAZ_CK(e, cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->cfg.device));
+    e->ta.chain_clk = (int)std::min<long long>(0x7fffffffll, (long long)microseconds * (long long)khz / 1000ll);
+    return 0;
+}
+
 int dbaz_search_set_mode(dbaz_engine* e, int32_t compact, int32_t max_inline) {
     if (!e) return 1;
     if (max_inline < 0) return fail(e, "max_inline must be >= 0");

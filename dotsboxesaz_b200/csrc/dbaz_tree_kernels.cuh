@@ -114,6 +114,7 @@ struct TreeArgs {
     int* ctr;
     int compact;          // 1: a tree's pending leaf goes to row atomicAdd(ctr[0]) instead of row == tree (pending == 1 only)
     int max_inline;       // > 0: at most this many simulations per tree and launch may finish without the net
+    int chain_clk;        // > 0: ... and none is started once the tree has spent this many SM clocks in the launch
     int batch_rows;       // compact mode: rows the evaluator of this launch will run; a leaf beyond them waits a wave
     // Overlapped chains (compact mode, dbaz_search_step2): a wave is two launches over two leaf batches 0 / 1.
     //   phase 1 "absorb": trees whose pending leaf sits in batch buf ^ 1 (just evaluated) are backed up and run on; trees in
@@ -894,6 +895,11 @@ __device__ __forceinline__ bool search_step_seq(const Board& b, const TreeArgs& 
     }
     T.flags &= ~TF_FIRST_WAVE;
     int inline_done = 0;
+    // A launch lasts as long as its longest chain.  Bounding the chains by COUNT makes a tree whose simulations are cheap
+    // (upper levels in L2, cache hits) stop as early as one whose every level waits for DRAM; bounding them by TIME lets
+    // the cheap ones run on while the launch is waiting for the expensive ones anyway.  Results do not depend on where a
+    // chain is cut (the next launch continues it), so the clock only shapes the schedule.
+    const long long t_start = ta.chain_clk > 0 ? clock64() : 0ll;
     while (T.sims_left > 0) {
         __syncwarp();  // stores of the previous backup must be visible to this selection's loads
         const int kind = tree_select<APL, NW, true>(b, ta, t, T, la, in, nullptr, lane);
@@ -934,6 +940,7 @@ __device__ __forceinline__ bool search_step_seq(const Board& b, const TreeArgs& 
             root_prior_mix<APL, NW>(b, ta, t, T, rh, noise, coeff, sh, lane);
         }
         if (ta.max_inline > 0 && ++inline_done >= ta.max_inline) break;
+        if (ta.chain_clk > 0 && clock64() - t_start > (long long)ta.chain_clk) break;
     }
     if (lane == 0) {
         if (leaf_kind && !compact) leaf_kind[t] = (int8_t)T.n_pending;

@@ -94,6 +94,10 @@ class Engine:
         self.compact = False
         self.max_inline = 0
         self.set_mode(False, 4)
+        # captured wave loops bound the in-kernel chains by TIME (microseconds per tree and launch; 0 = by count only,
+        # max_inline): see include/dbaz_b200.h, dbaz_search_set_chain_budget.  20 us measured best on configs[1] (8 .. 30 swept:
+        # +3 % sims/s over the count of 4) and in self-play (+6 % games/h); results do not depend on it.
+        self.chain_us = int(os.environ.get("DBAZ_CHAIN_US", "20"))
         self.eval_cache_log2 = 0
         self._counts_host = torch.zeros((64, 4), dtype=torch.int32).pin_memory()
         self._graph_pool = None
@@ -203,6 +207,11 @@ class Engine:
         if (bool(compact), int(max_inline)) != (self.compact, self.max_inline):
             self._ck(self.lib.dbaz_search_set_mode(self._h, 1 if compact else 0, int(max_inline)), launches=0)
             self.compact, self.max_inline = bool(compact), int(max_inline)
+
+    def set_chain_budget(self, microseconds):
+        """Time bound of the in-kernel chains for the launches that follow (0 = off): include/dbaz_b200.h,
+        dbaz_search_set_chain_budget.  The captured wave loops set their own (self.chain_us)."""
+        self._ck(self.lib.dbaz_search_set_chain_budget(self._h, int(microseconds)), launches=0)
 
     def wave_counts(self):
         """(rows the last step asked for, busy trees after it).  Synchronises the stream."""
@@ -713,8 +722,10 @@ class Engine:
                 self._fold_loop_counts()
                 self.lib.dbaz_search_loop_destroy(self._h, C.c_uint64(loop[0]))
 
+    CHAIN_COUNT_CAP = 64   # with a time budget the count only stops runaway chains
+
     def _mode_key(self):
-        return (self.compact, self.max_inline, self.eval_cache_log2)
+        return (self.compact, self.max_inline, self.eval_cache_log2, self.chain_us)
 
     def _capture(self, evaluator, graph_waves, noise, coeff, pending=1):
         # warm up the evaluator alone (allocator, cuDNN heuristics); no leaf is pending between searches,
@@ -751,9 +762,13 @@ class Engine:
         # small batches are the tail of a search, where a wave costs the evaluator's latency floor whatever it serves:
         # longer in-kernel chains there save whole waves (any bound gives the same results)
         inline = self.max_inline
+        factor = 1
         if self._batch_rows is not None and inline > 0:
-            inline *= 4 if self._batch_rows * 16 <= self.n_games else (2 if self._batch_rows * 4 <= self.n_games else 1)
+            factor = 4 if self._batch_rows * 16 <= self.n_games else (2 if self._batch_rows * 4 <= self.n_games else 1)
+        budget = int(self.chain_us) * factor if (inline > 0 and int(pending) == 1) else 0
+        inline = self.CHAIN_COUNT_CAP if budget > 0 else inline * factor
         self.lib.dbaz_search_set_mode(self._h, 1 if self.compact else 0, int(inline))
+        self._ck(self.lib.dbaz_search_set_chain_budget(self._h, budget), launches=0)
         self.lib.dbaz_search_begin(self._h, _ptr(self._idle_reads), int(pending), _ptr(noise), float(coeff), self._stream())
         g = torch.cuda.CUDAGraph(keep_graph=True) if self._batch_rows is not None else torch.cuda.CUDAGraph()
         n0, w0 = self._nl, self._nw
@@ -789,6 +804,7 @@ class Engine:
         self._nl, self._nw = n0, w0  # capture enqueues nothing
         self.lib.dbaz_search_set_batch_rows(self._h, 0)
         self.lib.dbaz_search_set_mode(self._h, 1 if self.compact else 0, int(self.max_inline))
+        self.lib.dbaz_search_set_chain_budget(self._h, 0)
         return g
 
     def root_visits(self):

@@ -216,6 +216,12 @@ int dbaz_search_status(dbaz_engine *e, int64_t *out8, uint64_t stream);
  * bound: a tree runs on until a leaf needs the net (the order of a tree's simulations, hence every result, is the
  * same for any setting). */
 int dbaz_search_set_mode(dbaz_engine *e, int32_t compact, int32_t max_inline);
+/* A second bound on the in-kernel chains of dbaz_search_set_mode: a tree starts no further net-free simulation once it has
+ * spent `microseconds` in a dbaz_search_step launch (0 = no time bound, the default).  A launch lasts as long as its longest
+ * chain; the time bound lets trees whose simulations are cheap run on while the launch waits for the expensive ones.  Like the
+ * count, it only shapes the schedule: results are the same for every value.  Captured launches keep the value they were
+ * captured with. */
+int dbaz_search_set_chain_budget(dbaz_engine *e, int32_t microseconds);
 /* Compact mode: the evaluator that follows the next dbaz_search_step() calls will run rows 0..rows-1 only
  * (0 = no limit).  A tree whose leaf would land beyond them drops that selection and repeats it in the next wave --
  * the selection wrote nothing but a lazily created child, so the repeat finds the same leaf over the same path and
