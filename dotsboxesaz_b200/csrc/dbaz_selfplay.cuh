@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(SP_WARPS * 32) k_selfplay_pick(Board b, TreeAr
         sp.h_moves[row] = move;
         sp.h_active[row] = 1;
         sp.moves[t] = move;
+        if (move < 0) sp.searching[t] = 0;  // a finished search without a single visit (cannot happen for a legal budget): the
+                                            // game stops here instead of being picked up again at every check
     }
 }
 
