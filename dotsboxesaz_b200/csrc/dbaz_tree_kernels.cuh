@@ -1030,7 +1030,11 @@ __device__ __forceinline__ bool search_step_waves(const Board& b, const TreeArgs
 // SEQ: max_pending_evals == 1 (search_step_seq); else the K-wave path.  Two kernels rather than one branch: each gets its
 // own register allocation and half the code.
 template <int APL, int NW, bool SEQ>
-__global__ void __launch_bounds__(TREE_WARPS * 32, (APL == 1 ? 28 : (APL == 2 ? 20 : 12)) / TREE_WARPS)
+// Resident trees per SM (= register cap): 28 -> 72 registers for one action per lane (3x3), 20 -> 102 for two; for three and
+// more (5x5: 168 registers uncapped, 12 trees per SM, 13 % of the warp slots) 16 -> 128 registers with 36 bytes of spills:
+// the kernel is latency-bound with nine waves of CTAs, so residency wins -- 139 -> 114 us per launch on configs[3] (20 -> 96
+// registers: 111 us, 156 bytes of spills).
+__global__ void __launch_bounds__(TREE_WARPS * 32, (APL == 1 ? 28 : (APL == 2 ? 20 : 16)) / TREE_WARPS)
 k_search_step(Board b, TreeArgs ta, int pending /* max_pending_evals of this search, <= ta.max_pending */,
               const float* __restrict__ priors, const float* __restrict__ values,
               const double* __restrict__ noise, double coeff, void* __restrict__ planes, int dtype, int layout,
